@@ -1,0 +1,239 @@
+/* tsdiff_b200 C-ABI -- the drop-in boundary for the LD eps-net hot path.
+ *
+ * Built from tsdiff_b200/csrc/ into tsdiff_b200/libtsdiff_b200.so for sm_100a.
+ * The reference (seonghann/tsdiff) has no FFI of its own: its hot path is Python calling
+ * third-party CUDA wheels.  Each entry point below replaces the group of reference
+ * functions cited next to it (paths relative to the reference root); INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted;
+ *  - nothing here allocates or frees caller memory; scratch comes in through the structs;
+ *  - every call is stream-ordered on `stream` (a cudaStream_t), never synchronises, and is
+ *    legal inside CUDA-graph stream capture (tsd_bond_order_build excepted: it memsets);
+ *  - return value: 0 = TSD_OK, otherwise a TSD_ERR_* code (tsd_error_string explains);
+ *  - edge counts live on the device (`num_edges`), kernels are launched at capacity and
+ *    exit early, so one captured graph serves every step of a sampling run.
+ */
+#ifndef TSDIFF_B200_H
+#define TSDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tsd_stream_t; /* cudaStream_t */
+
+enum {
+  TSD_OK = 0,
+  TSD_ERR_INVALID = 1,   /* bad argument (null pointer, unsupported size) */
+  TSD_ERR_CUDA = 2,      /* a CUDA runtime call failed; see tsd_last_cuda_error */
+  TSD_ERR_UNSUPPORTED = 3
+};
+
+enum { TSD_ACT_NONE = 0, TSD_ACT_RELU = 1, TSD_ACT_SWISH = 2, TSD_ACT_SSP = 3, TSD_ACT_SOFTPLUS = 4 };
+
+/* GEMM arithmetic for the per-edge / per-node linear layers */
+enum {
+  TSD_MATH_FP32 = 0, /* FFMA, fp32 in / fp32 accumulate: the 1e-4 parity path            */
+  TSD_MATH_TF32 = 1  /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM: looser bound    */
+};
+
+#define TSD_MAX_GRAPH_NODES 256 /* atoms per reaction graph supported by the tile builders */
+#define TSD_NUM_BOND_TYPES 22   /* len(utils.chem.BOND_TYPES), utils/chem.py:21 */
+
+/* nn.Linear: weight (out_features, in_features) row-major, bias (out_features) or NULL.
+ * Pointers go straight into the live nn.Parameter storage. */
+typedef struct {
+  const float* weight;
+  const float* bias;
+  int32_t in_features;
+  int32_t out_features;
+} tsd_linear_t;
+
+/* Static description of a batch of reaction graphs (built once per batch). */
+typedef struct {
+  int32_t num_nodes;        /* N */
+  int32_t num_graphs;       /* G */
+  int32_t max_graph_nodes;  /* max_g n_g (<= TSD_MAX_GRAPH_NODES) */
+  int32_t edge_capacity;    /* sum_g n_g (n_g - 1) */
+  const int32_t* graph_ptr; /* (G+1) first node of each graph; `batch` must be sorted */
+  const int32_t* pair_ptr;  /* (G+1) prefix of n_g^2: offset of graph g's n_g x n_g pair tables */
+  const int32_t* node_graph;/* (N) graph id of each node (= batch) */
+} tsd_batch_t;
+
+/* Per-step edge list in CSR form, written by tsd_edge_build. All arrays have
+ * `edge_capacity` entries; the first num_edges[0] are valid, sorted by (row, col). */
+typedef struct {
+  int32_t* num_edges;  /* (2) [0] = E of graph a, [1] = E of graph b (edges with in_b) */
+  int32_t* row;        /* edge_index[0] */
+  int32_t* col;        /* edge_index[1] */
+  float* length;       /* ||pos[row] - pos[col]|| */
+  int32_t* tab0;       /* pair table 0 value of the edge (0 for radius-only edges) */
+  int32_t* tab1;       /* pair table 1 value */
+  int32_t* in_b;       /* 1 if the edge also belongs to graph b */
+  int32_t* row_ptr;    /* (N+1) out-CSR over `row` */
+  int32_t* in_ptr;     /* (N+1) in-CSR: edges grouped by `col` (dst-sorted) */
+  int32_t* in_eid;     /* (E) edge ids sorted by (col, row) */
+  int32_t* graph_count;/* (G) scratch: edges per graph */
+} tsd_edges_t;
+
+const char* tsd_error_string(int code);
+int tsd_last_cuda_error(void);  /* cudaError_t of the last TSD_ERR_CUDA on this thread */
+int tsd_version(void);
+
+/* ---- K1: bond-order (k-hop) pair tables; position independent, once per batch -------------
+ * mode 0 (path B, replaces models/common.py:115-202 `_extend_ts_graph_order`): reactant
+ *   (type / 22) and product (type % 22) bond graphs are extended separately; table value =
+ *   type_r | type_p << 16 with bonds keeping their type and k-hop pairs (2 <= k <= order)
+ *   getting 22 + k - 1; 0 = not a local pair.  table_a uses order_a, table_b order_b.
+ * mode 1 (path A, replaces models/common.py:255-325 `_extend_graph_order`): one graph;
+ *   table_a = raw extended type (bond type, or 484 + k - 1); table_b = bond-embedding rows
+ *   row1 | row2 << 16 decoded as models/epsnet/dualenc.py:270-293 (ts_decode selects the TS
+ *   branch).  order_b is ignored.
+ * scratch: 2 * pair_ptr[G] int32.  Duplicate bond entries are summed like to_dense_adj. */
+int tsd_bond_order_build(int mode, const tsd_batch_t* batch, int32_t num_bonds,
+                         const int64_t* bond_index /* (2, num_bonds) */,
+                         const int64_t* bond_type /* (num_bonds) */,
+                         int32_t order_a, int32_t order_b, int32_t ts_decode,
+                         int32_t* table_a, int32_t* table_b, int32_t* scratch,
+                         int32_t* error_flag /* (1) device, set !=0 on cross-graph bonds */,
+                         tsd_stream_t stream);
+
+/* ---- K2: per-step edge list (replaces models/common.py:328-384 `_extend_to_radius_graph`,
+ * :205-223, :387-417 and models/epsnet/condensenc.py:117-154): radius graph per reaction
+ * (d^2 < cutoff^2 strict, first max_neighbors+1 in-range atoms per centre in index order,
+ * self included then dropped -- the torch_cluster CUDA rule) united with the local pairs of
+ * table 0, emitted row-major sorted with out- and in-CSR.  If tab1_is_graph, `in_b` marks
+ * edges of the second graph (local pairs of table 1 united with the same radius graph). */
+int tsd_edge_build(const tsd_batch_t* batch, const float* pos /* (N,3) */, double cutoff,
+                   int32_t max_neighbors, const int32_t* table0, const int32_t* table1,
+                   int32_t tab1_is_graph, const tsd_edges_t* edges, tsd_stream_t stream);
+
+/* ---- node embedding of path B (models/epsnet/condensenc.py:193-198):
+ * z = cat[emb[Z] + W r, W p - W r]  -> (N, 2*half) */
+int tsd_condensed_node_embed(int32_t num_nodes, const int64_t* atom_type, const int64_t* r_feat,
+                             const int64_t* p_feat, int32_t feat_dim, const float* atom_emb /* (100, half) */,
+                             const float* feat_weight /* (half, feat_dim) */, int32_t half, float* z,
+                             tsd_stream_t stream);
+
+/* nn.Embedding lookup (+ optional max_norm renormalisation IN PLACE on the looked-up rows,
+ * models/encoder/schnet.py:152; scale = max_norm / (norm + 1e-7)). max_norm <= 0 disables. */
+int tsd_embedding(int32_t num_nodes, const int64_t* index, float* weight /* (num_rows, dim) */,
+                  int32_t num_rows, int32_t dim, float max_norm, float* out /* (N, dim) */,
+                  tsd_stream_t stream);
+
+/* ---- K3: edge embedding (replaces models/encoder/edge.py:58-68 `MLPEdgeEncoder.forward`,
+ * and with `cat0` != NULL models/epsnet/condensenc.py:156-176 / dualenc.py:270-285):
+ *   d_emb = lin1(act(lin0(len)));  without cat: out = d_emb * bond_emb[code & 0xffff]
+ *   with cat: out = cat2(cat_act(cat0(cat[d_emb*bond_emb[code&0xffff], d_emb*bond_emb[code>>16]])))
+ * `d_emb` (E_cap, H) is scratch that is also an output: pass reuse_d_emb = 1 to skip
+ * recomputing it when only the codes changed (second graph of path B). */
+typedef struct {
+  tsd_linear_t lin0, lin1;       /* edge_encoder.mlp.layers.{0,1} */
+  const float* bond_emb;         /* edge_encoder.bond_emb.weight (100, H) */
+  int32_t act;                   /* config.mlp_act */
+  const tsd_linear_t* cat0;      /* edge_cat.0 (2H -> H) or NULL */
+  const tsd_linear_t* cat2;      /* edge_cat.2 (H -> H) */
+  int32_t cat_act;               /* config.edge_cat_act */
+} tsd_edge_encoder_t;
+
+int tsd_edge_embed(const tsd_batch_t* batch, const tsd_edges_t* edges, const int32_t* code,
+                   const tsd_edge_encoder_t* enc, int32_t reuse_d_emb, float* d_emb, float* tmp,
+                   float* out, int32_t math, tsd_stream_t stream);
+
+/* ---- K4: one SchNet InteractionBlock (replaces models/encoder/schnet.py:90-128):
+ *   W = (nn2(ssp(nn0(edge_attr)))) * C(len);  x1 = lin1(h_in);  agg_i = sum_{j->i} x1_j * W_ji
+ *   h_out = h_in + lin(ssp(lin2(agg)))
+ * C = [len <= cutoff] or the cosine cutoff when smooth.  Deterministic segmented reduction
+ * over the dst-sorted in-CSR (no atomics). scratch: ef (E_cap,H) x2, nf (N,H) x3. */
+typedef struct {
+  tsd_linear_t nn0, nn2, lin1, lin2, lin;
+  float cutoff;
+  int32_t smooth;
+} tsd_interaction_t;
+
+int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                     const tsd_interaction_t* blk, const float* h_in, float* h_out, float* ef0,
+                     float* ef1, float* nf0, float* nf1, float* nf2, int32_t math,
+                     tsd_stream_t stream);
+
+/* ---- K5: one GINEConv + GINEncoder glue (replaces models/encoder/gin.py:42-73,:136-143):
+ *   out_i = sum_{j->i, edge local} relu(h_j + e_ji) + (1 + eps) h_i;  hid = nn1(relu(nn0(out)))
+ *   h_out = (relu_after ? relu(hid) : hid) + h_in
+ * Only edges with edges->tab0 != 0 (local edges) take part. */
+typedef struct {
+  tsd_linear_t nn0, nn1;
+  const float* eps; /* (1) buffer */
+  int32_t relu_after;
+} tsd_gine_t;
+
+int tsd_gine_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                   const tsd_gine_t* conv, const float* h_in, float* h_out, float* nf0, float* nf1,
+                   int32_t math, tsd_stream_t stream);
+
+/* ---- K6: pair features + output MLP (replaces models/common.py:226-229 and :78-90 as
+ * grad_dist_mlp / grad_{global,local}_dist_mlp):
+ *   edge_inv = l2(act(l1(act(l0(cat[h_row * h_col, edge_attr])))))
+ * accumulate != 0 adds into edge_inv (ensemble sum, models/sampler.py:96-109). */
+typedef struct {
+  tsd_linear_t l0, l1, l2;
+  int32_t act;
+} tsd_pair_mlp_t;
+
+int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* h,
+                 const float* edge_attr, const tsd_pair_mlp_t* mlp, int32_t accumulate, float* ef0,
+                 float* edge_inv, int32_t math, tsd_stream_t stream);
+
+/* ---- K7: eq_transform + clip + Langevin update + centring + NaN flag, one launch
+ * (replaces models/geometry.py:22-30, models/sampler.py:208-254 LD branch, :260-268 and
+ * models/epsnet/dualenc.py:827-849,946-965).
+ * Per step k (read from *step_counter, which the kernel post-increments):
+ *   score_c = clip_c(eq_transform(inv_c / inv_div, edges selected by mask_c))  for channel c
+ *   eps = score_0 + (use1[k] ? w1 * score_1 : 0)
+ *   pos = center(pos + step_size[k] * eps / sigma[k] + noise * noise_scale[k])
+ * noise: external tensor (n_steps, N, 3) if given, else Philox4x32-10 keyed by
+ * (seed, step, atom_offset + atom) + Box-Muller.  mask mode: 0 all edges, 1 tab != 0, 2 tab == 0. */
+typedef struct {
+  const float* inv;     /* (E) or NULL to disable the channel */
+  const int32_t* mask;  /* (E) */
+  int32_t mask_mode;
+  float clip;           /* <= 0: no clipping */
+  float weight;
+} tsd_score_channel_t;
+
+typedef struct {
+  const float* sched;      /* (num_steps, 4): step_size, sigma, noise_scale, use_channel1 */
+  int32_t num_steps;       /* rows of sched / noise; steps beyond it are no-ops */
+  int32_t* step_counter;   /* (1) device */
+  int32_t* ticket;         /* (1) device scratch, zero-initialised once */
+  int32_t* nan_flag;       /* (1) device, sticky */
+  const float* noise;      /* (n_steps, N, 3) or NULL -> Philox */
+  uint64_t seed;
+  int64_t atom_offset;     /* global index of this shard's first atom */
+  float inv_div;           /* ensemble size M (edge_inv /= M, sampler.py:111) */
+  float clip_pos;          /* <= 0: none */
+  float* traj;             /* (traj_steps, N, 3) or NULL */
+  int32_t traj_steps;      /* rows of traj */
+  int32_t traj_base_step;  /* traj slot = step - traj_base_step (skipped when out of range) */
+} tsd_ld_params_t;
+
+int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, float* pos,
+                const tsd_score_channel_t* ch0, const tsd_score_channel_t* ch1,
+                const tsd_ld_params_t* ld, tsd_stream_t stream);
+
+/* eq_transform alone (models/geometry.py:22-30), used by the API-level tests. */
+int tsd_eq_transform(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* pos,
+                     const tsd_score_channel_t* ch, float inv_div, float* node_eq /* (N,3) */,
+                     tsd_stream_t stream);
+
+/* Philox4x32-10 + Box-Muller normals exactly as tsd_ld_step draws them: out (N,3). */
+int tsd_philox_normal(int32_t num_nodes, uint64_t seed, int32_t step, int64_t atom_offset,
+                      float* out, tsd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDIFF_B200_H */

@@ -1,0 +1,45 @@
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "reference: needs the read-only reference checkout (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return torch.load(os.path.join(GOLDEN, "golden_outputs.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def rxn0():
+    return torch.load(os.path.join(GOLDEN, "rxn0_graph.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def syn4():
+    return torch.load(os.path.join(GOLDEN, "syn4_graph.pt"), weights_only=False)
+
+
+def graph_for(name, rxn0, syn4):
+    return rxn0 if "rxn0" in name else syn4

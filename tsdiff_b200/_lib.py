@@ -1,0 +1,131 @@
+"""ctypes binding of include/tsdiff_b200.h (libtsdiff_b200.so).
+
+The product path fails loudly when the CUDA library is missing or a call returns an
+error; there is no CPU or PyTorch fallback anywhere behind these functions."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtsdiff_b200.so")
+
+ACT = {"none": 0, "relu": 1, "ReLU": 1, "swish": 2, "ssp": 3, "softplus": 4, "Softplus": 4}
+MATH = {"fp32": 0, "tf32": 1}
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f32p = C.POINTER(C.c_float)
+
+
+class Linear(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("in_features", C.c_int32),
+                ("out_features", C.c_int32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("num_graphs", C.c_int32), ("max_graph_nodes", C.c_int32),
+                ("edge_capacity", C.c_int32), ("graph_ptr", C.c_void_p), ("pair_ptr", C.c_void_p),
+                ("node_graph", C.c_void_p)]
+
+
+class Edges(C.Structure):
+    _fields_ = [("num_edges", C.c_void_p), ("row", C.c_void_p), ("col", C.c_void_p), ("length", C.c_void_p),
+                ("tab0", C.c_void_p), ("tab1", C.c_void_p), ("in_b", C.c_void_p), ("row_ptr", C.c_void_p),
+                ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p), ("graph_count", C.c_void_p)]
+
+
+class EdgeEncoder(C.Structure):
+    _fields_ = [("lin0", Linear), ("lin1", Linear), ("bond_emb", C.c_void_p), ("act", C.c_int32),
+                ("cat0", C.POINTER(Linear)), ("cat2", C.POINTER(Linear)), ("cat_act", C.c_int32)]
+
+
+class Interaction(C.Structure):
+    _fields_ = [("nn0", Linear), ("nn2", Linear), ("lin1", Linear), ("lin2", Linear), ("lin", Linear),
+                ("cutoff", C.c_float), ("smooth", C.c_int32)]
+
+
+class Gine(C.Structure):
+    _fields_ = [("nn0", Linear), ("nn1", Linear), ("eps", C.c_void_p), ("relu_after", C.c_int32)]
+
+
+class PairMlp(C.Structure):
+    _fields_ = [("l0", Linear), ("l1", Linear), ("l2", Linear), ("act", C.c_int32)]
+
+
+class ScoreChannel(C.Structure):
+    _fields_ = [("inv", C.c_void_p), ("mask", C.c_void_p), ("mask_mode", C.c_int32), ("clip", C.c_float),
+                ("weight", C.c_float)]
+
+
+class LdParams(C.Structure):
+    _fields_ = [("sched", C.c_void_p), ("num_steps", C.c_int32), ("step_counter", C.c_void_p),
+                ("ticket", C.c_void_p), ("nan_flag", C.c_void_p), ("noise", C.c_void_p), ("seed", C.c_uint64),
+                ("atom_offset", C.c_int64), ("inv_div", C.c_float), ("clip_pos", C.c_float), ("traj", C.c_void_p),
+                ("traj_steps", C.c_int32), ("traj_base_step", C.c_int32)]
+
+
+# symbol -> argtypes; every function returns int (0 = TSD_OK) unless listed in _RESTYPES
+_P = C.c_void_p
+_SIGNATURES = {
+    "tsd_version": [],
+    "tsd_last_cuda_error": [],
+    "tsd_error_string": [C.c_int],
+    "tsd_bond_order_build": [C.c_int, C.POINTER(Batch), C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P,
+                             _P, _P, _P],
+    "tsd_edge_build": [C.POINTER(Batch), _P, C.c_double, C.c_int32, _P, _P, C.c_int32, C.POINTER(Edges), _P],
+    "tsd_condensed_node_embed": [C.c_int32, _P, _P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P],
+    "tsd_embedding": [C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_float, _P, _P],
+    "tsd_edge_embed": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(EdgeEncoder), C.c_int32, _P, _P, _P,
+                       C.c_int32, _P],
+    "tsd_cfconv_layer": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Interaction), _P, _P, _P, _P, _P, _P, _P,
+                         C.c_int32, _P],
+    "tsd_gine_layer": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Gine), _P, _P, _P, _P, C.c_int32, _P],
+    "tsd_pair_mlp": [C.POINTER(Batch), C.POINTER(Edges), _P, _P, C.POINTER(PairMlp), C.c_int32, _P, _P, C.c_int32,
+                     _P],
+    "tsd_ld_step": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.POINTER(ScoreChannel),
+                    C.POINTER(LdParams), _P],
+    "tsd_eq_transform": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.c_float, _P, _P],
+    "tsd_philox_normal": [C.c_int32, C.c_uint64, C.c_int32, C.c_int64, _P, _P],
+}
+_RESTYPES = {"tsd_error_string": C.c_char_p}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class TsdError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built -- run
+    `python -c "import __graft_entry__ as g; g.build()"` or `python tsdiff_b200/build.py`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TsdError("%s is missing: build it with `python tsdiff_b200/build.py` (needs nvcc); "
+                       "tsdiff_b200 has no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library drifted apart
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        lib = load()
+        msg = lib.tsd_error_string(rc)
+        raise TsdError("%s failed: %s (code %d)" % (what, msg.decode() if msg else "?", rc))
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, None -> NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def linear(weight, bias=None):
+    assert weight.is_contiguous() and (bias is None or bias.is_contiguous())
+    return Linear(weight.data_ptr(), bias.data_ptr() if bias is not None else None, weight.shape[1], weight.shape[0])

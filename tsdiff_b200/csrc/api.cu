@@ -1,0 +1,213 @@
+// C-ABI entry points that compose the kernels into the reference's operator granularity
+// (edge embedding, one SchNet interaction, one GINE conv, the output MLP).  See
+// include/tsdiff_b200.h for the contract and the reference lines each call replaces.
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+int tsd_launch_cfconv_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
+                                const float* x1, const float* filt, float* agg, cudaStream_t s);
+int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
+                              const int* local_tab, const float* h, const float* ea, const float* eps, float* out,
+                              cudaStream_t s);
+
+static thread_local int g_last_cuda_error = 0;
+
+int tsd_record_cuda_error(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return TSD_ERR_CUDA;
+}
+
+extern "C" int tsd_last_cuda_error(void) { return g_last_cuda_error; }
+extern "C" int tsd_version(void) { return 100; }
+
+extern "C" const char* tsd_error_string(int code) {
+  switch (code) {
+    case TSD_OK: return "ok";
+    case TSD_ERR_INVALID: return "invalid argument";
+    case TSD_ERR_CUDA: return cudaGetErrorString((cudaError_t)g_last_cuda_error);
+    case TSD_ERR_UNSUPPORTED: return "unsupported shape or mode";
+    default: return "unknown error";
+  }
+}
+
+int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream) {
+  if (math == TSD_MATH_TF32) {
+    int rc = tsd_gemm_tf32(g, stream);
+    if (rc != TSD_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core kernel does not take run on FFMA
+  }
+  return tsd_gemm_ffma(g, stream);
+}
+
+#define TSD_TRY(expr)        \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != TSD_OK) return _rc; \
+  } while (0)
+
+static GemmArgs edge_gemm(const tsd_batch_t* b, const tsd_edges_t* e, const tsd_linear_t& lin) {
+  GemmArgs g = tsd_gemm_args();
+  g.M_cap = b->edge_capacity;
+  g.M_ptr = e->num_edges;
+  g.N = lin.out_features;
+  g.K = lin.in_features;
+  g.W = lin.weight;
+  g.bias = lin.bias;
+  g.ldc = g.N;
+  g.lda = g.K;
+  return g;
+}
+
+static GemmArgs node_gemm(const tsd_batch_t* b, const tsd_linear_t& lin) {
+  GemmArgs g = tsd_gemm_args();
+  g.M_cap = b->num_nodes;
+  g.N = lin.out_features;
+  g.K = lin.in_features;
+  g.W = lin.weight;
+  g.bias = lin.bias;
+  g.ldc = g.N;
+  g.lda = g.K;
+  return g;
+}
+
+extern "C" int tsd_edge_embed(const tsd_batch_t* batch, const tsd_edges_t* edges, const int32_t* code,
+                              const tsd_edge_encoder_t* enc, int32_t reuse_d_emb, float* d_emb, float* tmp, float* out,
+                              int32_t math, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && code && enc && out && enc->bond_emb && enc->lin0.weight && enc->lin0.bias &&
+              enc->lin1.weight);
+  const int H = enc->lin1.out_features;
+  TSD_REQUIRE(enc->lin0.in_features == 1 && enc->lin0.out_features == enc->lin1.in_features);
+  cudaStream_t s = tsd_cu(stream);
+  const bool cat = enc->cat0 != nullptr;
+  if (!cat || !reuse_d_emb) {
+    GemmArgs g = edge_gemm(batch, edges, enc->lin1);
+    g.a_kind = TSD_A_EDGE_MLP0;
+    g.len = edges->length;
+    g.w0 = enc->lin0.weight;
+    g.b0 = enc->lin0.bias;
+    g.act0 = enc->act;
+    g.H = H;
+    if (cat) {
+      TSD_REQUIRE(d_emb);
+      g.C = d_emb;
+    } else {  // edge.py:66-68: d_emb * bond_emb[type]
+      g.mul_emb = enc->bond_emb;
+      g.mul_code = code;
+      g.C = out;
+    }
+    TSD_TRY(tsd_gemm(g, math, s));
+  }
+  if (cat) {
+    TSD_REQUIRE(enc->cat2 && tmp && d_emb);
+    TSD_REQUIRE(enc->cat0->in_features == 2 * H && enc->cat0->out_features == H);
+    GemmArgs g = edge_gemm(batch, edges, *enc->cat0);
+    g.a_kind = TSD_A_CAT;
+    g.A = d_emb;
+    g.lda = H;
+    g.H = H;
+    g.emb = enc->bond_emb;
+    g.code = code;
+    g.act = enc->cat_act;
+    g.C = tmp;
+    TSD_TRY(tsd_gemm(g, math, s));
+    GemmArgs g2 = edge_gemm(batch, edges, *enc->cat2);
+    g2.A = tmp;
+    g2.C = out;
+    TSD_TRY(tsd_gemm(g2, math, s));
+  }
+  return TSD_OK;
+}
+
+extern "C" int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                                const tsd_interaction_t* blk, const float* h_in, float* h_out, float* ef0, float* ef1,
+                                float* nf0, float* nf1, float* nf2, int32_t math, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && edge_attr && blk && h_in && h_out && ef0 && ef1 && nf0 && nf1 && nf2);
+  cudaStream_t s = tsd_cu(stream);
+  const int F = blk->nn2.out_features;
+  TSD_REQUIRE(blk->lin1.out_features == F && blk->lin2.in_features == F);
+  // filter network on the edges: W = nn2(ssp(nn0(edge_attr))) * C(len)
+  GemmArgs g = edge_gemm(batch, edges, blk->nn0);
+  g.A = edge_attr;
+  g.act = TSD_ACT_SSP;
+  g.C = ef0;
+  TSD_TRY(tsd_gemm(g, math, s));
+  g = edge_gemm(batch, edges, blk->nn2);
+  g.A = ef0;
+  g.scale_len = edges->length;
+  g.cutoff = blk->cutoff;
+  g.smooth = blk->smooth;
+  g.C = ef1;
+  TSD_TRY(tsd_gemm(g, math, s));
+  // x1 = lin1(h) (no bias)
+  g = node_gemm(batch, blk->lin1);
+  g.A = h_in;
+  g.C = nf0;
+  TSD_TRY(tsd_gemm(g, math, s));
+  TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, F, edges->in_ptr, edges->in_eid, edges->row, nf0, ef1, nf1, s));
+  // h_out = h_in + lin(ssp(lin2(agg)))
+  g = node_gemm(batch, blk->lin2);
+  g.A = nf1;
+  g.act = TSD_ACT_SSP;
+  g.C = nf2;
+  TSD_TRY(tsd_gemm(g, math, s));
+  g = node_gemm(batch, blk->lin);
+  g.A = nf2;
+  g.residual = h_in;
+  g.ldr = blk->lin.out_features;
+  g.C = h_out;
+  TSD_TRY(tsd_gemm(g, math, s));
+  return TSD_OK;
+}
+
+extern "C" int tsd_gine_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                              const tsd_gine_t* conv, const float* h_in, float* h_out, float* nf0, float* nf1,
+                              int32_t math, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && edge_attr && conv && conv->eps && h_in && h_out && nf0 && nf1);
+  cudaStream_t s = tsd_cu(stream);
+  const int H = conv->nn0.in_features;
+  TSD_TRY(tsd_launch_gine_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->row, edges->tab0, h_in,
+                                    edge_attr, conv->eps, nf0, s));
+  GemmArgs g = node_gemm(batch, conv->nn0);
+  g.A = nf0;
+  g.act = TSD_ACT_RELU;
+  g.C = nf1;
+  TSD_TRY(tsd_gemm(g, math, s));
+  g = node_gemm(batch, conv->nn1);
+  g.A = nf1;
+  g.act = conv->relu_after ? TSD_ACT_RELU : TSD_ACT_NONE;
+  g.residual = h_in;
+  g.ldr = conv->nn1.out_features;
+  g.C = h_out;
+  TSD_TRY(tsd_gemm(g, math, s));
+  return TSD_OK;
+}
+
+extern "C" int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* h, const float* edge_attr,
+                            const tsd_pair_mlp_t* mlp, int32_t accumulate, float* ef0, float* edge_inv, int32_t math,
+                            tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && h && edge_attr && mlp && ef0 && edge_inv);
+  TSD_REQUIRE(mlp->l2.out_features == 1 && mlp->l2.in_features == mlp->l1.out_features);
+  cudaStream_t s = tsd_cu(stream);
+  const int H = mlp->l0.in_features / 2;
+  GemmArgs g = edge_gemm(batch, edges, mlp->l0);
+  g.a_kind = TSD_A_PAIR;
+  g.A = edge_attr;
+  g.lda = H;
+  g.H = H;
+  g.h = h;
+  g.row = edges->row;
+  g.col = edges->col;
+  g.act = mlp->act;
+  g.C = ef0;
+  TSD_TRY(tsd_gemm(g, math, s));
+  g = edge_gemm(batch, edges, mlp->l1);
+  g.A = ef0;
+  g.act = mlp->act;
+  g.w3 = mlp->l2.weight;
+  g.b3 = mlp->l2.bias;
+  g.out_vec = edge_inv;
+  g.accumulate = accumulate;
+  TSD_TRY(tsd_gemm(g, math, s));
+  return TSD_OK;
+}

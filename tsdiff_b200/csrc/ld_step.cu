@@ -1,0 +1,213 @@
+// K7: eq_transform + clip_norm + Langevin update + NaN flag + per-graph centring in ONE
+// launch, one CTA per reaction graph, one thread per atom.  Reads the per-step scalars
+// from a device table indexed by a device step counter, so the same captured CUDA graph is
+// replayed for every step with no host round-trip.
+//
+// Replaces models/geometry.py:22-30 (eq_transform), models/sampler.py:208-254 (LD branch,
+// NaN check, center_pos, clip_pos, trajectory append), :260-268 and the two-channel
+// variant of models/epsnet/dualenc.py:827-849,946-965.
+//
+// Per atom the two scatter_add sums of eq_transform are accumulated sequentially in edge
+// order (out-edges by col, in-edges by row) -- the association order of a sequential
+// scatter over the row-major sorted edge list -- so results are deterministic.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 tsd_philox4x32_10(uint4 c, uint2 k) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+// three standard normals for (seed, step, global atom id): counter = (atom_lo, atom_hi, step, 0),
+// key = (seed_lo, seed_hi); Box-Muller on 24-bit uniforms in (0, 1).
+__device__ __forceinline__ float3 tsd_philox_normal3(uint64_t seed, int step, int64_t atom) {
+  uint4 r = tsd_philox4x32_10(make_uint4((unsigned)atom, (unsigned)((uint64_t)atom >> 32), (unsigned)step, 0u),
+                              make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  const float s = 1.0f / 16777216.0f;
+  float u0 = ((float)(r.x >> 8) + 0.5f) * s, u1 = ((float)(r.y >> 8) + 0.5f) * s;
+  float u2 = ((float)(r.z >> 8) + 0.5f) * s, u3 = ((float)(r.w >> 8) + 0.5f) * s;
+  const float two_pi = 6.283185307179586f;
+  float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+  return make_float3(ra * cosf(two_pi * u1), ra * sinf(two_pi * u1), rb * cosf(two_pi * u3));
+}
+
+__global__ void k_philox_normal(int num_nodes, uint64_t seed, int step, int64_t atom_offset, float* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_nodes) return;
+  float3 z = tsd_philox_normal3(seed, step, atom_offset + i);
+  out[3 * i] = z.x;
+  out[3 * i + 1] = z.y;
+  out[3 * i + 2] = z.z;
+}
+
+extern "C" int tsd_philox_normal(int32_t num_nodes, uint64_t seed, int32_t step, int64_t atom_offset, float* out,
+                                 tsd_stream_t stream) {
+  TSD_REQUIRE(out);
+  if (num_nodes == 0) return TSD_OK;
+  k_philox_normal<<<tsd_ceil_div(num_nodes, 256), 256, 0, tsd_cu(stream)>>>(num_nodes, seed, step, atom_offset, out);
+  TSD_LAUNCH_CHECK();
+  return TSD_OK;
+}
+
+// ------------------------------------------------------------------------------ eq_transform
+__device__ __forceinline__ bool tsd_edge_selected(const tsd_score_channel_t& ch, int e) {
+  if (ch.mask_mode == 0 || ch.mask == nullptr) return true;
+  int v = ch.mask[e];
+  return ch.mask_mode == 1 ? (v != 0) : (v == 0);
+}
+
+// score of atom `i` (global index): sum_{row=i} u*s - sum_{col=i} u*s, u = (p_row - p_col)/len.
+// spos holds the graph's positions (local index = global - n0).
+__device__ float3 tsd_node_score(const tsd_score_channel_t& ch, const tsd_edges_t& e, const float* spos, int n0, int i,
+                                 float inv_div) {
+  const float px = spos[3 * (i - n0)], py = spos[3 * (i - n0) + 1], pz = spos[3 * (i - n0) + 2];
+  float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+  for (int k = e.row_ptr[i]; k < e.row_ptr[i + 1]; ++k) {
+    if (!tsd_edge_selected(ch, k)) continue;
+    int c = e.col[k] - n0;
+    float inv_len = __fdiv_rn(1.0f, e.length[k]);
+    float s = __fdiv_rn(ch.inv[k], inv_div);
+    ax = __fadd_rn(ax, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(px, spos[3 * c])), s));
+    ay = __fadd_rn(ay, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(py, spos[3 * c + 1])), s));
+    az = __fadd_rn(az, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(pz, spos[3 * c + 2])), s));
+  }
+  for (int k = e.in_ptr[i]; k < e.in_ptr[i + 1]; ++k) {
+    int id = e.in_eid[k];
+    if (!tsd_edge_selected(ch, id)) continue;
+    int r = e.row[id] - n0;
+    float inv_len = __fdiv_rn(1.0f, e.length[id]);
+    float s = __fdiv_rn(ch.inv[id], inv_div);
+    bx = __fadd_rn(bx, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r], px)), s));
+    by = __fadd_rn(by, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 1], py)), s));
+    bz = __fadd_rn(bz, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 2], pz)), s));
+  }
+  return make_float3(__fadd_rn(ax, bx), __fadd_rn(ay, by), __fadd_rn(az, bz));
+}
+
+// sampler.py:265-268
+__device__ __forceinline__ float3 tsd_clip_norm(float3 v, float limit) {
+  if (limit <= 0.f) return v;
+  float norm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
+  float denom = norm > limit ? __fdiv_rn(limit, norm) : 1.0f;
+  return make_float3(__fmul_rn(v.x, denom), __fmul_rn(v.y, denom), __fmul_rn(v.z, denom));
+}
+
+__global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_eq_transform(tsd_batch_t b, tsd_edges_t e,
+                                                                     const float* __restrict__ pos,
+                                                                     tsd_score_channel_t ch, float inv_div,
+                                                                     float* __restrict__ node_eq) {
+  __shared__ float spos[3 * TSD_MAX_GRAPH_NODES];
+  const int n0 = b.graph_ptr[blockIdx.x], n = b.graph_ptr[blockIdx.x + 1] - n0;
+  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) spos[i] = pos[(size_t)3 * n0 + i];
+  __syncthreads();
+  for (int li = threadIdx.x; li < n; li += blockDim.x) {
+    float3 s = tsd_node_score(ch, e, spos, n0, n0 + li, inv_div);
+    node_eq[3 * (n0 + li)] = s.x;
+    node_eq[3 * (n0 + li) + 1] = s.y;
+    node_eq[3 * (n0 + li) + 2] = s.z;
+  }
+}
+
+extern "C" int tsd_eq_transform(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* pos,
+                                const tsd_score_channel_t* ch, float inv_div, float* node_eq, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && pos && ch && ch->inv && node_eq);
+  if (batch->num_graphs == 0) return TSD_OK;
+  k_eq_transform<<<batch->num_graphs, TSD_MAX_GRAPH_NODES, 0, tsd_cu(stream)>>>(*batch, *edges, pos, *ch, inv_div, node_eq);
+  TSD_LAUNCH_CHECK();
+  return TSD_OK;
+}
+
+// ------------------------------------------------------------------------------------- K7
+__global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, tsd_edges_t e, float* __restrict__ pos,
+                                                                tsd_score_channel_t ch0, tsd_score_channel_t ch1,
+                                                                tsd_ld_params_t ld) {
+  __shared__ float spos[3 * TSD_MAX_GRAPH_NODES];
+  __shared__ float snew[3 * TSD_MAX_GRAPH_NODES];
+  __shared__ float smean[3];
+  __shared__ int sstep;
+  const int g = blockIdx.x;
+  const int n0 = b.graph_ptr[g], n = b.graph_ptr[g + 1] - n0;
+  if (threadIdx.x == 0) sstep = *reinterpret_cast<volatile int*>(ld.step_counter);
+  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) spos[i] = pos[(size_t)3 * n0 + i];
+  __syncthreads();
+  const int step = sstep;
+  if (step < ld.num_steps) {
+    const float step_size = ld.sched[4 * step], sigma = ld.sched[4 * step + 1], nscale = ld.sched[4 * step + 2];
+    const bool use1 = ch1.inv != nullptr && ld.sched[4 * step + 3] != 0.f;
+    for (int li = threadIdx.x; li < n; li += blockDim.x) {
+      const int i = n0 + li;
+      float3 eps = tsd_clip_norm(tsd_node_score(ch0, e, spos, n0, i, ld.inv_div), ch0.clip);
+      if (use1) {
+        float3 g1 = tsd_clip_norm(tsd_node_score(ch1, e, spos, n0, i, ld.inv_div), ch1.clip);
+        eps.x = __fadd_rn(eps.x, __fmul_rn(g1.x, ch1.weight));
+        eps.y = __fadd_rn(eps.y, __fmul_rn(g1.y, ch1.weight));
+        eps.z = __fadd_rn(eps.z, __fmul_rn(g1.z, ch1.weight));
+      }
+      float3 z;
+      if (ld.noise) {
+        const float* zp = ld.noise + ((size_t)step * b.num_nodes + i) * 3;
+        z = make_float3(zp[0], zp[1], zp[2]);
+      } else {
+        z = tsd_philox_normal3(ld.seed, step, ld.atom_offset + i);
+      }
+      // pos + step_size * eps / sigma + noise * sqrt(2 step_size)   (sampler.py:239-244)
+      float nx = __fadd_rn(__fadd_rn(spos[3 * li], __fdiv_rn(__fmul_rn(step_size, eps.x), sigma)), __fmul_rn(z.x, nscale));
+      float ny = __fadd_rn(__fadd_rn(spos[3 * li + 1], __fdiv_rn(__fmul_rn(step_size, eps.y), sigma)), __fmul_rn(z.y, nscale));
+      float nz = __fadd_rn(__fadd_rn(spos[3 * li + 2], __fdiv_rn(__fmul_rn(step_size, eps.z), sigma)), __fmul_rn(z.z, nscale));
+      if (isnan(nx) || isnan(ny) || isnan(nz)) atomicOr(ld.nan_flag, 1);
+      snew[3 * li] = nx;
+      snew[3 * li + 1] = ny;
+      snew[3 * li + 2] = nz;
+    }
+    __syncthreads();
+    // center_pos: subtract the per-graph mean (sequential sum in atom order, like scatter_mean)
+    if (threadIdx.x < 3) {
+      float s = 0.f;
+      for (int li = 0; li < n; ++li) s = __fadd_rn(s, snew[3 * li + threadIdx.x]);
+      smean[threadIdx.x] = __fdiv_rn(s, (float)max(n, 1));
+    }
+    __syncthreads();
+    const int slot = step - ld.traj_base_step;
+    float* traj = (ld.traj && slot >= 0 && slot < ld.traj_steps) ? ld.traj + (size_t)slot * b.num_nodes * 3 : nullptr;
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) {
+      float v = __fsub_rn(snew[i], smean[i % 3]);
+      if (ld.clip_pos > 0.f) v = fminf(fmaxf(v, -ld.clip_pos), ld.clip_pos);
+      pos[(size_t)3 * n0 + i] = v;
+      if (traj) traj[(size_t)3 * n0 + i] = v;
+    }
+  }
+  // last CTA out advances the step counter (every CTA has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int t = atomicAdd(ld.ticket, 1);
+    if (t == (int)gridDim.x - 1) {
+      *ld.ticket = 0;
+      *ld.step_counter = step + 1;
+      __threadfence();
+    }
+  }
+}
+
+extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, float* pos, const tsd_score_channel_t* ch0,
+                           const tsd_score_channel_t* ch1, const tsd_ld_params_t* ld, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && pos && ch0 && ch0->inv && ld && ld->sched && ld->step_counter && ld->ticket &&
+              ld->nan_flag);
+  TSD_REQUIRE(batch->max_graph_nodes <= TSD_MAX_GRAPH_NODES);
+  if (batch->num_graphs == 0) return TSD_OK;
+  tsd_score_channel_t off;
+  memset(&off, 0, sizeof(off));
+  int threads = ((batch->max_graph_nodes + 31) / 32) * 32;
+  if (threads < 32) threads = 32;
+  k_ld_step<<<batch->num_graphs, threads, 0, tsd_cu(stream)>>>(*batch, *edges, pos, *ch0, ch1 ? *ch1 : off, *ld);
+  TSD_LAUNCH_CHECK();
+  return TSD_OK;
+}

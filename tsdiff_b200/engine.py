@@ -1,0 +1,429 @@
+"""Host-side driver of the CUDA library: owns device buffers (through torch), binds the
+live nn.Parameter storage into the C structs, and issues the kernel sequence of one
+eps-net evaluation / one Langevin step on torch's current stream (so the whole step can be
+captured in a CUDA graph and replayed with no host round-trip).
+
+torch is plumbing here (allocation, streams, graphs); every arithmetic op is a kernel of
+libtsdiff_b200.so.  Nothing in this module falls back to PyTorch math.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise L.TsdError("%s must be a CUDA tensor: tsdiff_b200 has no CPU path" % name)
+
+
+class BatchPlan:
+    """Everything about a batch of reaction graphs that does not depend on positions:
+    graph offsets, the bond-order pair tables (K1) and the capacity-sized edge arrays that
+    K2 refills every step.  mode 0 = TS / condensenc tables, mode 1 = dualenc tables."""
+
+    def __init__(self, mode, batch, bond_index, bond_type, order_a, order_b=0, ts_decode=False):
+        lib = L.load()
+        _require_cuda(batch, "batch")
+        dev = batch.device
+        self.device = dev
+        self.mode = mode
+        batch = batch.contiguous()
+        n = batch.numel()
+        counts = torch.bincount(batch) if n else torch.zeros(0, dtype=torch.long, device=dev)
+        counts_h = counts.cpu()
+        if n and not bool((batch[1:] >= batch[:-1]).all()):
+            raise ValueError("`batch` must be sorted (PyG Batch contract)")
+        if n and int(counts_h.min()) == 0:
+            raise ValueError("empty graphs are not supported")
+        g = counts_h.numel()
+        self.num_nodes, self.num_graphs = n, g
+        self.max_graph_nodes = int(counts_h.max()) if g else 1
+        if self.max_graph_nodes > 256:
+            raise L.TsdError("graphs with more than 256 atoms are not supported (got %d)" % self.max_graph_nodes)
+        self.edge_capacity = int((counts_h * (counts_h - 1)).sum()) if g else 0
+        self.num_pairs = int((counts_h * counts_h).sum()) if g else 0
+        i32 = dict(dtype=torch.int32, device=dev)
+        gp = torch.zeros(g + 1, dtype=torch.long)
+        pp = torch.zeros(g + 1, dtype=torch.long)
+        if g:
+            gp[1:] = counts_h.cumsum(0)
+            pp[1:] = (counts_h * counts_h).cumsum(0)
+        self.graph_ptr = gp.to(**i32)
+        self.pair_ptr = pp.to(**i32)
+        self.node_graph = batch.to(torch.int32)
+        self.counts = counts_h
+        self.c_batch = L.Batch(n, g, self.max_graph_nodes, self.edge_capacity, self.graph_ptr.data_ptr(),
+                               self.pair_ptr.data_ptr(), self.node_graph.data_ptr())
+
+        # ---- K1: bond-order pair tables
+        self.table_a = torch.zeros(max(self.num_pairs, 1), **i32)
+        self.table_b = torch.zeros(max(self.num_pairs, 1), **i32)
+        scratch = torch.empty(max(2 * self.num_pairs, 1), **i32)
+        err = torch.zeros(1, **i32)
+        bond_index = bond_index.to(device=dev, dtype=torch.long).contiguous()
+        bond_type = bond_type.to(device=dev, dtype=torch.long).contiguous()
+        L.check(lib.tsd_bond_order_build(mode, C.byref(self.c_batch), bond_index.size(1), L.ptr(bond_index),
+                                         L.ptr(bond_type), order_a, max(order_b, 1), int(ts_decode),
+                                         L.ptr(self.table_a), L.ptr(self.table_b), L.ptr(scratch), L.ptr(err),
+                                         _stream()), "tsd_bond_order_build")
+        code = int(err.item())
+        if code:
+            raise ValueError("bond_index/bond_type invalid for this batch (flag %d: 1 = index or type out of "
+                             "range, 2 = bond across two graphs)" % code)
+
+        # ---- K2 outputs, capacity sized
+        cap = max(self.edge_capacity, 1)
+        self.num_edges = torch.zeros(2, **i32)
+        self.row = torch.zeros(cap, **i32)
+        self.col = torch.zeros(cap, **i32)
+        self.length = torch.ones(cap, dtype=torch.float32, device=dev)
+        self.tab0 = torch.zeros(cap, **i32)
+        self.tab1 = torch.zeros(cap, **i32)
+        self.in_b = torch.zeros(cap, **i32)
+        self.row_ptr = torch.zeros(n + 1, **i32)
+        self.in_ptr = torch.zeros(n + 1, **i32)
+        self.in_eid = torch.zeros(cap, **i32)
+        self.graph_count = torch.zeros(max(g, 1), **i32)
+        self.c_edges = L.Edges(*[t.data_ptr() for t in (
+            self.num_edges, self.row, self.col, self.length, self.tab0, self.tab1, self.in_b, self.row_ptr,
+            self.in_ptr, self.in_eid, self.graph_count)])
+
+    def build_edges(self, pos, cutoff, max_neighbors=32):
+        """K2: refill the edge list for the current positions (no sync)."""
+        lib = L.load()
+        assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape == (self.num_nodes, 3)
+        L.check(lib.tsd_edge_build(C.byref(self.c_batch), L.ptr(pos), float(cutoff), int(max_neighbors),
+                                   L.ptr(self.table_a), L.ptr(self.table_b), 1 if self.mode == 0 else 0,
+                                   C.byref(self.c_edges), _stream()), "tsd_edge_build")
+
+    def edge_count(self):
+        return int(self.num_edges[0].item())  # synchronises; API-level use only
+
+
+class _Scratch:
+    """Capacity-sized activation buffers shared by all ensemble members."""
+
+    def __init__(self, plan, hidden, n_edge_bufs, n_node_bufs):
+        dev = plan.device
+        cap = max(plan.edge_capacity, 1)
+        self.edge = [torch.empty(cap, hidden, dtype=torch.float32, device=dev) for _ in range(n_edge_bufs)]
+        self.node = [torch.empty(max(plan.num_nodes, 1), hidden, dtype=torch.float32, device=dev)
+                     for _ in range(n_node_bufs)]
+
+
+def _edge_encoder_struct(enc, act, cat=None, cat_act="none"):
+    """enc: layers.MLPEdgeEncoder; cat: nn.Sequential(Linear, act, Linear) or None."""
+    keep = []
+    s = L.EdgeEncoder()
+    s.lin0 = L.linear(enc.mlp.layers[0].weight, enc.mlp.layers[0].bias)
+    s.lin1 = L.linear(enc.mlp.layers[1].weight, enc.mlp.layers[1].bias)
+    s.bond_emb = enc.bond_emb.weight.data_ptr()
+    s.act = L.ACT[act]
+    if cat is not None:
+        c0 = L.linear(cat[0].weight, cat[0].bias)
+        c2 = L.linear(cat[2].weight, cat[2].bias)
+        keep += [c0, c2]
+        s.cat0 = C.pointer(c0)
+        s.cat2 = C.pointer(c2)
+        s.cat_act = L.ACT[cat_act]
+    return s, keep
+
+
+def _interaction_struct(blk):
+    s = L.Interaction()
+    s.nn0 = L.linear(blk.conv.nn[0].weight, blk.conv.nn[0].bias)
+    s.nn2 = L.linear(blk.conv.nn[2].weight, blk.conv.nn[2].bias)
+    s.lin1 = L.linear(blk.conv.lin1.weight, None)
+    s.lin2 = L.linear(blk.conv.lin2.weight, blk.conv.lin2.bias)
+    s.lin = L.linear(blk.lin.weight, blk.lin.bias)
+    s.cutoff = float(blk.conv.cutoff)
+    s.smooth = int(bool(blk.conv.smooth))
+    return s
+
+
+def _pair_mlp_struct(mlp):
+    s = L.PairMlp()
+    s.l0 = L.linear(mlp.layers[0].weight, mlp.layers[0].bias)
+    s.l1 = L.linear(mlp.layers[1].weight, mlp.layers[1].bias)
+    s.l2 = L.linear(mlp.layers[2].weight, mlp.layers[2].bias)
+    s.act = L.ACT[mlp.act]
+    return s
+
+
+def _gine_struct(conv, relu_after):
+    s = L.Gine()
+    s.nn0 = L.linear(conv.nn.layers[0].weight, conv.nn.layers[0].bias)
+    s.nn1 = L.linear(conv.nn.layers[1].weight, conv.nn.layers[1].bias)
+    s.eps = conv.eps.data_ptr()
+    s.relu_after = int(relu_after)
+    return s
+
+
+class CondensedScoreEngine:
+    """Path B: eps-net evaluation of an ensemble of CondenseEncoderEpsNetwork members on one
+    BatchPlan (models/epsnet/condensenc.py:178-239 per member, models/sampler.py:58-116 for
+    the ensemble sum).  `edge_inv` holds the SUM over members; consumers divide by M."""
+
+    def __init__(self, models, atom_type, r_feat, p_feat, bond_index, bond_type, batch, math="fp32"):
+        lib = L.load()
+        cfg = models[0].config
+        self.models = list(models)
+        self.cfg = cfg
+        self.math = L.MATH[math]
+        for t, nm in ((atom_type, "atom_type"), (r_feat, "r_feat"), (p_feat, "p_feat"), (batch, "batch")):
+            _require_cuda(t, nm)
+        for m in self.models:
+            if next(m.parameters()).device != batch.device:
+                raise L.TsdError("model parameters and inputs must live on the same CUDA device")
+        self.plan = BatchPlan(0, batch, bond_index, bond_type, int(cfg.edge_order), int(cfg.pred_edge_order))
+        self.two_graphs = int(cfg.edge_order) != int(cfg.pred_edge_order)
+        plan = self.plan
+        h = int(cfg.hidden_dim)
+        self.hidden = h
+        self.cutoff = float(cfg.edge_cutoff)
+        # d_emb, tmp, ea1, ea2, ef0, ef1
+        self.ws = _Scratch(plan, h, 6, 4)
+        self.edge_inv = torch.zeros(max(plan.edge_capacity, 1), dtype=torch.float32, device=plan.device)
+        atom_type = atom_type.to(torch.long).contiguous()
+        r_feat = r_feat.to(torch.long).contiguous()
+        p_feat = p_feat.to(torch.long).contiguous()
+        self.members = []
+        for m in self.models:
+            z = torch.empty(max(plan.num_nodes, 1), h, dtype=torch.float32, device=plan.device)
+            L.check(lib.tsd_condensed_node_embed(plan.num_nodes, L.ptr(atom_type), L.ptr(r_feat), L.ptr(p_feat),
+                                                 r_feat.size(1) if r_feat.dim() == 2 else int(cfg.feat_dim),
+                                                 L.ptr(m.atom_embedding.weight), L.ptr(m.atom_feat_embedding.weight),
+                                                 h // 2, L.ptr(z), _stream()), "tsd_condensed_node_embed")
+            enc, keep = _edge_encoder_struct(m.edge_encoder, m.edge_encoder.mlp.act, m.edge_cat,
+                                             L_act(cfg.edge_cat_act))
+            blocks = [_interaction_struct(b) for b in m.encoder.interactions]
+            pair = _pair_mlp_struct(m.grad_dist_mlp)
+            self.members.append({"z": z, "enc": enc, "keep": keep, "blocks": blocks, "pair": pair})
+
+    def evaluate(self, pos):
+        """One ensemble eps-net evaluation at `pos`; fills plan edges and self.edge_inv (sum
+        over members, on the edges of graph a; consumers select graph b with plan.in_b)."""
+        lib = L.load()
+        plan, ws, s = self.plan, self.ws, _stream()
+        b, e = C.byref(plan.c_batch), C.byref(plan.c_edges)
+        d_emb, tmp, ea1, ea2, ef0, ef1 = ws.edge
+        hbuf, nf0, nf1, nf2 = ws.node
+        plan.build_edges(pos, self.cutoff)
+        for mi, mem in enumerate(self.members):
+            enc = C.byref(mem["enc"])
+            L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab0), enc, 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea1),
+                                       self.math, s), "tsd_edge_embed")
+            h_in = mem["z"]
+            for blk in mem["blocks"]:
+                L.check(lib.tsd_cfconv_layer(b, e, L.ptr(ea1), C.byref(blk), L.ptr(h_in), L.ptr(hbuf), L.ptr(ef0),
+                                             L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2), self.math, s),
+                        "tsd_cfconv_layer")
+                h_in = hbuf
+            if self.two_graphs:
+                L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea2),
+                                           self.math, s), "tsd_edge_embed")
+                ea_out = ea2
+            else:
+                ea_out = ea1
+            L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_out), C.byref(mem["pair"]), 1 if mi > 0 else 0,
+                                     L.ptr(ef0), L.ptr(self.edge_inv), self.math, s), "tsd_pair_mlp")
+
+    def score_channels(self, clip):
+        ch0 = L.ScoreChannel(self.edge_inv.data_ptr(), self.plan.in_b.data_ptr(), 1 if self.two_graphs else 0,
+                             float(clip) if clip is not None else 0.0, 1.0)
+        return ch0, None
+
+    @property
+    def num_members(self):
+        return len(self.members)
+
+
+def L_act(name):
+    from .models.layers import activation_name
+    return activation_name(name)
+
+
+class DualScoreEngine:
+    """Path A: DualEncoderEpsNetwork evaluation (models/epsnet/dualenc.py:206-374, type
+    'diffusion').  Global SchNet on all edges, local GIN on edges with type > 0."""
+
+    def __init__(self, model, atom_type, bond_index, bond_type, batch, math="fp32"):
+        lib = L.load()
+        cfg = model.config
+        self.model, self.cfg = model, cfg
+        self.math = L.MATH[math]
+        _require_cuda(atom_type, "atom_type")
+        _require_cuda(batch, "batch")
+        self.ts = bool(getattr(model, "TS", False))
+        self.plan = BatchPlan(1, batch, bond_index, bond_type, int(cfg.edge_order), 0, ts_decode=self.ts)
+        plan = self.plan
+        h = int(cfg.hidden_dim)
+        self.hidden = h
+        self.cutoff = float(cfg.cutoff)
+        self.ws = _Scratch(plan, h, 6, 5)
+        cap = max(plan.edge_capacity, 1)
+        self.edge_inv_global = torch.zeros(cap, dtype=torch.float32, device=plan.device)
+        self.edge_inv_local = torch.zeros(cap, dtype=torch.float32, device=plan.device)
+        self.atom_type = atom_type.to(torch.long).contiguous()
+        act = model.edge_encoder_global.mlp.act
+        cat_act = L_act(cfg.edge_cat_act) if self.ts else "none"
+        self.enc_g, self._k1 = _edge_encoder_struct(model.edge_encoder_global, act,
+                                                    model.edge_cat_global if self.ts else None, cat_act)
+        self.enc_l, self._k2 = _edge_encoder_struct(model.edge_encoder_local, act,
+                                                    model.edge_cat_local if self.ts else None, cat_act)
+        self.blocks = [_interaction_struct(b) for b in model.encoder_global.interactions]
+        n_local = len(model.encoder_local.convs)
+        self.gines = [_gine_struct(c, i < n_local - 1) for i, c in enumerate(model.encoder_local.convs)]
+        self.pair_g = _pair_mlp_struct(model.grad_global_dist_mlp)
+        self.pair_l = _pair_mlp_struct(model.grad_local_dist_mlp)
+        n = max(plan.num_nodes, 1)
+        self.h0_global = torch.empty(n, h, dtype=torch.float32, device=plan.device)
+        self.h0_local = torch.empty(n, h, dtype=torch.float32, device=plan.device)
+        self.refresh_embeddings()
+
+    def refresh_embeddings(self):
+        """node_emb lookups (weights are constant during sampling).  The global embedding has
+        max_norm=10: looked-up rows are renormalised IN PLACE like nn.Embedding does."""
+        lib = L.load()
+        m, plan = self.model, self.plan
+        wg = m.encoder_global.node_emb.weight
+        L.check(lib.tsd_embedding(plan.num_nodes, L.ptr(self.atom_type), L.ptr(wg), wg.size(0), wg.size(1), 10.0,
+                                  L.ptr(self.h0_global), _stream()), "tsd_embedding")
+        wl = m.encoder_local.node_emb.weight
+        L.check(lib.tsd_embedding(plan.num_nodes, L.ptr(self.atom_type), L.ptr(wl), wl.size(0), wl.size(1), 0.0,
+                                  L.ptr(self.h0_local), _stream()), "tsd_embedding")
+
+    def evaluate(self, pos):
+        lib = L.load()
+        plan, ws, s = self.plan, self.ws, _stream()
+        b, e = C.byref(plan.c_batch), C.byref(plan.c_edges)
+        d_emb, tmp, ea_g, ea_l, ef0, ef1 = ws.edge
+        hbuf, nf0, nf1, nf2, hloc = ws.node
+        plan.build_edges(pos, self.cutoff)
+        codes = L.ptr(plan.tab1)
+        # global: edge encoder -> SchNet -> pair MLP on every edge
+        L.check(lib.tsd_edge_embed(b, e, codes, C.byref(self.enc_g), 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea_g),
+                                   self.math, s), "tsd_edge_embed")
+        h_in = self.h0_global
+        for blk in self.blocks:
+            L.check(lib.tsd_cfconv_layer(b, e, L.ptr(ea_g), C.byref(blk), L.ptr(h_in), L.ptr(hbuf), L.ptr(ef0),
+                                         L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2), self.math, s),
+                    "tsd_cfconv_layer")
+            h_in = hbuf
+        L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
+                                 L.ptr(self.edge_inv_global), self.math, s), "tsd_pair_mlp")
+        # local: edge encoder on all edges, GIN + pair MLP restricted to type > 0 by masks
+        L.check(lib.tsd_edge_embed(b, e, codes, C.byref(self.enc_l), 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea_l),
+                                   self.math, s), "tsd_edge_embed")
+        h_in = self.h0_local
+        for gc in self.gines:
+            L.check(lib.tsd_gine_layer(b, e, L.ptr(ea_l), C.byref(gc), L.ptr(h_in), L.ptr(hloc), L.ptr(nf0),
+                                       L.ptr(nf1), self.math, s), "tsd_gine_layer")
+            h_in = hloc
+        L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_l), C.byref(self.pair_l), 0, L.ptr(ef0),
+                                 L.ptr(self.edge_inv_local), self.math, s), "tsd_pair_mlp")
+
+    def score_channels(self, clip, clip_local, w_global):
+        """dualenc.py:827-849: local score on type > 0 edges (+ optional clip_local); global
+        score on the remaining edges, clipped, weighted by w_global."""
+        ch0 = L.ScoreChannel(self.edge_inv_local.data_ptr(), self.plan.tab0.data_ptr(), 1,
+                             float(clip_local) if clip_local is not None else 0.0, 1.0)
+        ch1 = L.ScoreChannel(self.edge_inv_global.data_ptr(), self.plan.tab0.data_ptr(), 2,
+                             float(clip) if clip is not None else 0.0, float(w_global))
+        return ch0, ch1
+
+    num_members = 1
+
+
+class LangevinRunner:
+    """Runs the Langevin loop for either engine: per step [K2, eps-net kernels, K7], captured
+    once in a CUDA graph and replayed; per-step scalars come from a device table indexed by
+    a device step counter (the score net ignores the time step)."""
+
+    def __init__(self, engine, ch0, ch1, sched, pos, noise=None, seed=0, atom_offset=0, clip_pos=None,
+                 keep_traj=True, use_graph=True):
+        self.engine, self.plan = engine, engine.plan
+        dev = self.plan.device
+        self.n_steps = sched.size(0)
+        self.sched = sched.to(device=dev, dtype=torch.float32).contiguous()
+        self.pos = pos
+        self.pos0 = pos.clone()
+        self.noise = None if noise is None else noise.to(device=dev, dtype=torch.float32).contiguous()
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.step_counter = torch.zeros(1, **i32)
+        self.ticket = torch.zeros(1, **i32)
+        self.nan_flag = torch.zeros(1, **i32)
+        self.traj = (torch.empty(self.n_steps, self.plan.num_nodes, 3, dtype=torch.float32, device=dev)
+                     if keep_traj else None)
+        self.ch0, self.ch1 = ch0, ch1
+        self.ld = L.LdParams(
+            self.sched.data_ptr(), self.n_steps, self.step_counter.data_ptr(), self.ticket.data_ptr(),
+            self.nan_flag.data_ptr(), self.noise.data_ptr() if self.noise is not None else None,
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(atom_offset), float(engine.num_members),
+            float(clip_pos) if clip_pos is not None else 0.0,
+            self.traj.data_ptr() if self.traj is not None else None, self.n_steps if keep_traj else 0, 0)
+        self.use_graph = use_graph
+        self.graph = None
+
+    def _one_step(self):
+        lib = L.load()
+        self.engine.evaluate(self.pos)
+        L.check(lib.tsd_ld_step(C.byref(self.plan.c_batch), C.byref(self.plan.c_edges), L.ptr(self.pos),
+                                C.byref(self.ch0), C.byref(self.ch1) if self.ch1 is not None else None,
+                                C.byref(self.ld), _stream()), "tsd_ld_step")
+
+    def _reset(self):
+        self.pos.copy_(self.pos0)
+        self.step_counter.zero_()
+        self.ticket.zero_()
+        self.nan_flag.zero_()
+
+    def prepare(self):
+        """Warm up (loads kernels, outside capture) and capture one step."""
+        if not self.use_graph or self.graph is not None:
+            return
+        side = torch.cuda.Stream(device=self.plan.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._one_step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._one_step()
+        self._reset()
+
+    def run(self, n_steps=None, check_every=0):
+        """Advance n_steps (default: all).  Raises FloatingPointError like sampler.py:248-250 /
+        dualenc.py:959-961 if a NaN position was produced (checked after the chunk)."""
+        n = self.n_steps if n_steps is None else n_steps
+        self.prepare()
+        for k in range(n):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._one_step()
+            if check_every and (k + 1) % check_every == 0 and int(self.nan_flag.item()):
+                raise FloatingPointError()
+        if int(self.nan_flag.item()):
+            raise FloatingPointError()
+        return self.pos
+
+
+def ld_schedule(alphas, n_steps, step_lr, global_start_sigma=float("inf")):
+    """(n_steps, 4) table [step_size, sigma, sqrt(2 step_size), use_global] for i = T-1 ... T-n_steps
+    computed with the reference's own fp32 torch expressions (sampler.py:143,239-243):
+    step_size = step_lr * (sigmas[i] / 0.01) ** 2."""
+    alphas = alphas.detach().float().cpu()
+    sigmas = (1.0 - alphas).sqrt() / alphas.sqrt()
+    t = sigmas.numel()
+    idx = torch.arange(t - 1, t - 1 - n_steps, -1)
+    sig = sigmas[idx]
+    step_size = step_lr * (sig / 0.01) ** 2
+    out = torch.stack([step_size, sig, torch.sqrt(step_size * 2), (sig < global_start_sigma).float()], dim=1)
+    return out.contiguous(), sigmas

@@ -1,0 +1,73 @@
+"""CondenseEncoderEpsNetwork (path B) -- host-side mirror of the reference class
+models/epsnet/condensenc.py:47-328: same constructor argument, attribute names, parameter
+registration order (=> identical state_dict keys and seeded init), same `forward`
+signature and return contract.  The arithmetic runs in the CUDA library."""
+import os
+
+import torch
+from torch import nn
+
+from ... import engine as E
+from ..layers import (MultiLayerPerceptron, Marker, activation_name, get_edge_encoder, load_encoder,
+                      schedule_parameters, NUM_BOND_TYPES)
+from ._cache import EngineCache
+
+
+class CondenseEncoderEpsNetwork(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.edge_encoder = get_edge_encoder(config)
+        assert config.hidden_dim % 2 == 0
+        self.atom_embedding = nn.Embedding(100, config.hidden_dim // 2)
+        self.atom_feat_embedding = nn.Linear(config.feat_dim, config.hidden_dim // 2, bias=False)
+        self.encoder = load_encoder(config, "encoder")
+        self.grad_dist_mlp = MultiLayerPerceptron(
+            2 * config.hidden_dim, [config.hidden_dim, config.hidden_dim // 2, 1], activation=config.mlp_act)
+        # aliases registered a second time, exactly like condensenc.py:81-89 (state_dict carries
+        # `model_embedding.*` / `model.*` duplicates of the same tensors)
+        self.model_embedding = nn.ModuleList([self.atom_embedding, self.atom_feat_embedding])
+        self.model = nn.ModuleList([self.edge_encoder, self.encoder, self.grad_dist_mlp])
+        self.betas, self.alphas = schedule_parameters(config)
+        self.num_timesteps = self.betas.size(0)
+        self.num_bond_types = NUM_BOND_TYPES
+        ch = self.edge_encoder.out_channels
+        self.edge_cat = nn.Sequential(nn.Linear(ch * 2, ch), Marker(activation_name(config.edge_cat_act)),
+                                      nn.Linear(ch, ch))
+        self.math = os.environ.get("TSDIFF_B200_MATH", "fp32")
+        self._cache = EngineCache()
+
+    def _engine(self, atom_type, r_feat, p_feat, bond_index, bond_type, batch):
+        return self._cache.get(
+            (atom_type, r_feat, p_feat, bond_index, bond_type, batch), (self.math,),
+            lambda: E.CondensedScoreEngine([self], atom_type, r_feat, p_feat, bond_index, bond_type, batch,
+                                           math=self.math))
+
+    @torch.no_grad()
+    def forward(self, atom_type, r_feat, p_feat, pos, bond_index, bond_type, batch, time_step=None,
+                return_edges=True, **kwargs):
+        """condensenc.py:241-265.  `time_step` is accepted and ignored, as in the reference
+        (condensenc.py:250-258).  Returns (edge_inv (E,1), edge_index (2,E) int64 row-major
+        sorted, edge_length (E,1)) on the pred_edge_order graph."""
+        eng = self._engine(atom_type, r_feat, p_feat, bond_index, bond_type, batch)
+        pos = pos.detach().to(torch.float32).contiguous()
+        eng.evaluate(pos)
+        return condensed_outputs(eng, return_edges)
+
+    def get_loss(self, *args, **kwargs):
+        raise NotImplementedError(
+            "training (condensenc.py:267-328) needs the backward kernels: SURVEY.md section 8(f)-2, not built yet")
+
+
+def condensed_outputs(eng, return_edges=True, divide=1):
+    """Compacts the capacity-sized device buffers into the reference's return contract."""
+    plan = eng.plan
+    e = plan.edge_count()
+    sel = plan.in_b[:e].bool() if eng.two_graphs else torch.ones(e, dtype=torch.bool, device=plan.device)
+    edge_inv = eng.edge_inv[:e][sel].unsqueeze(-1)
+    if divide != 1:
+        edge_inv = edge_inv / divide
+    if not return_edges:
+        return edge_inv
+    edge_index = torch.stack([plan.row[:e][sel], plan.col[:e][sel]], dim=0).long()
+    return edge_inv, edge_index, plan.length[:e][sel].unsqueeze(-1)

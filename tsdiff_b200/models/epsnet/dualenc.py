@@ -1,0 +1,111 @@
+"""DualEncoderEpsNetwork (path A) -- host-side mirror of models/epsnet/dualenc.py:62-374 and
+its Langevin sampler :687-967 (`type: diffusion`, sampling_type 'ld').  Same constructor,
+attribute names / state_dict layout, `forward` and `langevin_dynamics_sample` signatures;
+compute is in the CUDA library."""
+import os
+
+import torch
+from torch import nn
+
+from ... import engine as E
+from ..layers import (GINEncoder, Marker, MultiLayerPerceptron, SchNetEncoder, activation_name, get_edge_encoder,
+                      schedule_parameters, NUM_BOND_TYPES)
+from ._cache import EngineCache
+
+
+class DualEncoderEpsNetwork(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.edge_encoder_global = get_edge_encoder(config)
+        self.edge_encoder_local = get_edge_encoder(config)
+        self.encoder_global = SchNetEncoder(
+            hidden_channels=config.hidden_dim, num_filters=config.hidden_dim, num_interactions=config.num_convs,
+            edge_channels=self.edge_encoder_global.out_channels, cutoff=config.cutoff, smooth=config.smooth_conv,
+            embedding=True)
+        self.encoder_local = GINEncoder(hidden_dim=config.hidden_dim, num_convs=config.num_convs_local,
+                                        embedding=True)
+        self.grad_global_dist_mlp = MultiLayerPerceptron(
+            2 * config.hidden_dim, [config.hidden_dim, config.hidden_dim // 2, 1], activation=config.mlp_act)
+        self.grad_local_dist_mlp = MultiLayerPerceptron(
+            2 * config.hidden_dim, [config.hidden_dim, config.hidden_dim // 2, 1], activation=config.mlp_act)
+        self.model_type = config.type
+        if self.model_type == "diffusion":
+            self.betas, self.alphas = schedule_parameters(config)
+            self.num_timesteps = self.betas.size(0)
+        else:
+            raise NotImplementedError("model type %r: only 'diffusion' is on the LD hot path" % (self.model_type,))
+        self.TS = config.TS if hasattr(config, "TS") else False
+        self.num_bond_types = NUM_BOND_TYPES
+        global_modules = [self.edge_encoder_global, self.encoder_global, self.grad_global_dist_mlp]
+        local_modules = [self.edge_encoder_local, self.encoder_local, self.grad_local_dist_mlp]
+        if self.TS:
+            ch = self.edge_encoder_global.out_channels
+            act = activation_name(config.edge_cat_act)
+            self.edge_cat_global = nn.Sequential(nn.Linear(ch * 2, ch), Marker(act), nn.Linear(ch, ch))
+            self.edge_cat_local = nn.Sequential(nn.Linear(ch * 2, ch), Marker(act), nn.Linear(ch, ch))
+            global_modules.append(self.edge_cat_global)
+            local_modules.append(self.edge_cat_local)
+        self.model_global = nn.ModuleList(global_modules)
+        self.model_local = nn.ModuleList(local_modules)
+        self.math = os.environ.get("TSDIFF_B200_MATH", "fp32")
+        self._cache = EngineCache()
+
+    def _engine(self, atom_type, bond_index, bond_type, batch):
+        return self._cache.get((atom_type, bond_index, bond_type, batch), (self.math,),
+                               lambda: E.DualScoreEngine(self, atom_type, bond_index, bond_type, batch,
+                                                         math=self.math))
+
+    @torch.no_grad()
+    def forward(self, atom_type, pos, bond_index, bond_type, batch, time_step=None, edge_index=None,
+                edge_type=None, edge_length=None, return_edges=False, extend_order=True, extend_radius=True,
+                is_sidechain=None):
+        """dualenc.py:206-374.  Returns (edge_inv_global (E,1), edge_inv_local (E_l,1)) and, with
+        return_edges, (edge_index, edge_type, edge_length, local_edge_mask)."""
+        if edge_index is not None or edge_type is not None or edge_length is not None:
+            raise NotImplementedError("precomputed edges: the CUDA path always rebuilds the graph (dualenc.py:230)")
+        if not (extend_order and extend_radius) or is_sidechain is not None:
+            raise NotImplementedError("extend_order/extend_radius=False and is_sidechain are outside the LD hot path")
+        eng = self._engine(atom_type, bond_index, bond_type, batch)
+        eng.refresh_embeddings()  # nn.Embedding(max_norm) renormalises on every lookup
+        eng.evaluate(pos.detach().to(torch.float32).contiguous())
+        plan = eng.plan
+        e = plan.edge_count()
+        etype = plan.tab0[:e].long()
+        local = etype > 0
+        inv_g = eng.edge_inv_global[:e].unsqueeze(-1).clone()
+        inv_l = eng.edge_inv_local[:e][local].unsqueeze(-1)
+        if not return_edges:
+            return inv_g, inv_l
+        edge_index = torch.stack([plan.row[:e], plan.col[:e]], dim=0).long()
+        return inv_g, inv_l, edge_index, etype, plan.length[:e].unsqueeze(-1).clone(), local
+
+    def get_loss(self, *args, **kwargs):
+        raise NotImplementedError(
+            "training (dualenc.py:376-562) needs the backward kernels: SURVEY.md section 8(f)-2, not built yet")
+
+    def langevin_dynamics_sample(self, atom_type, pos_init, bond_index, bond_type, batch, num_graphs, extend_order,
+                                 extend_radius=True, n_steps=100, step_lr=0.0000010, clip=1000, clip_local=None,
+                                 clip_pos=None, min_sigma=0, is_sidechain=None, global_start_sigma=float("inf"),
+                                 w_global=0.2, w_reg=1.0, **kwargs):
+        """dualenc.py:687-967 with sampling_type='ld' (:946-952).  Extra keyword-only knobs that
+        do not exist in the reference: noise= (n_steps,N,3) tensor replacing torch.randn_like,
+        seed= Philox seed, keep_traj=, atom_offset= (global index of this shard's first atom)."""
+        sampling_type = kwargs.get("sampling_type", "ddpm_noisy")
+        if sampling_type != "ld":
+            raise NotImplementedError("sampling_type %r: only 'ld' is on the hot path (SURVEY.md 8(f)-3)"
+                                      % (sampling_type,))
+        if is_sidechain is not None or not (extend_order and extend_radius):
+            raise NotImplementedError("is_sidechain / extend_*=False are outside the LD hot path")
+        eng = self._engine(atom_type, bond_index, bond_type, batch)
+        eng.refresh_embeddings()
+        sched, sigmas = E.ld_schedule(self.alphas, n_steps, step_lr, global_start_sigma)
+        pos = (pos_init.detach().to(torch.float32) * sigmas[-1].to(pos_init.device)).contiguous()
+        ch0, ch1 = eng.score_channels(clip, clip_local, w_global)
+        runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, noise=kwargs.get("noise"),
+                                  seed=kwargs.get("seed", torch.initial_seed()),
+                                  atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
+                                  keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True))
+        pos = runner.run()
+        traj = list(runner.traj.cpu().unbind(0)) if runner.traj is not None else []
+        return pos, traj

@@ -1,0 +1,67 @@
+"""EnsembleSampler -- host-side mirror of models/sampler.py:44-257: same constructor,
+attributes (`models`, `config`, `alphas`, `betas`, `num_timesteps`), `forward` and
+`dynamic_sampling` signatures and return contract.  The Langevin loop (`sampling_type='ld'`,
+sampler.py:238-244) runs as a replayed CUDA graph with no per-step host work."""
+import torch
+from torch import nn
+
+from .. import engine as E
+from .epsnet._cache import EngineCache
+from .epsnet.condensenc import condensed_outputs
+
+
+class EnsembleSampler(nn.Module):
+    def __init__(self, models):
+        super().__init__()
+        self.models = models
+        self.config = models[0].config
+        self.alphas = models[0].alphas
+        self.betas = models[0].betas
+        self.num_timesteps = models[0].num_timesteps
+        self.math = getattr(models[0], "math", "fp32")
+        self._cache = EngineCache()
+
+    def _engine(self, atom_type, r_feat, p_feat, bond_index, bond_type, batch):
+        return self._cache.get(
+            (atom_type, r_feat, p_feat, bond_index, bond_type, batch), (self.math, len(self.models)),
+            lambda: E.CondensedScoreEngine(self.models, atom_type, r_feat, p_feat, bond_index, bond_type, batch,
+                                           math=self.math))
+
+    @torch.no_grad()
+    def forward(self, atom_type, r_feat, p_feat, pos, bond_index, bond_type, batch, time_step=None,
+                return_edges=True, **kwargs):
+        """sampler.py:58-116: mean of edge_inv over the members; edges from member 0."""
+        eng = self._engine(atom_type, r_feat, p_feat, bond_index, bond_type, batch)
+        eng.evaluate(pos.detach().to(torch.float32).contiguous())
+        return condensed_outputs(eng, return_edges, divide=len(self.models))
+
+    def dynamic_sampling(self, atom_type, r_feat, p_feat, pos_init, bond_index, bond_type, batch, num_graphs,
+                         extend_order, extend_radius=True, n_steps=100, step_lr=0.0000010, clip=1000, clip_pos=None,
+                         denoise_from_time_t=None, noise_from_time_t=None, **kwargs):
+        """sampler.py:118-257 for sampling_type='ld'.  Returns (pos on device, list of n_steps
+        CPU (N,3) tensors).  Raises FloatingPointError when a NaN position appears.
+        Keyword-only extras absent from the reference: noise= (n_steps,N,3) tensor used instead
+        of torch.randn_like; seed= Philox seed (default torch.initial_seed()); keep_traj=;
+        atom_offset= global index of the first atom of this shard; use_graph=."""
+        sampling_type = kwargs.get("sampling_type", "ddpm")
+        if sampling_type != "ld":
+            raise NotImplementedError("sampling_type %r: only 'ld' is on the hot path (SURVEY.md 8(f)-3)"
+                                      % (sampling_type,))
+        if noise_from_time_t is not None:
+            raise NotImplementedError("from_ts_guess noising (sampler.py:149-167) is SURVEY.md 8(f)-3 scope")
+        eng = self._engine(atom_type, r_feat, p_feat, bond_index, bond_type, batch)
+        t_end = self.num_timesteps if denoise_from_time_t is None else int(denoise_from_time_t)
+        assert t_end >= n_steps
+        sched, sigmas = E.ld_schedule(self.alphas[:t_end], n_steps, step_lr)
+        pos = pos_init.detach().to(torch.float32)
+        if denoise_from_time_t is None:
+            pos = pos * sigmas[-1].to(pos.device)  # sampler.py:182
+        pos = pos.contiguous().clone()
+        ch0, ch1 = eng.score_channels(clip)
+        runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, noise=kwargs.get("noise"),
+                                  seed=kwargs.get("seed", torch.initial_seed()),
+                                  atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
+                                  keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True))
+        pos = runner.run()
+        traj = list(runner.traj.cpu().unbind(0)) if runner.traj is not None else []
+        return pos, traj
