@@ -83,6 +83,8 @@ typedef struct {
 const char* tsd_error_string(int code);
 int tsd_last_cuda_error(void);  /* cudaError_t of the last TSD_ERR_CUDA on this thread */
 int tsd_version(void);
+/* number of kernel launches this library has issued (host counter; bench.py's gpu_launches) */
+int64_t tsd_launch_count(void);
 
 /* ---- K1: bond-order (k-hop) pair tables; position independent, once per batch -------------
  * mode 0 (path B, replaces models/common.py:115-202 `_extend_ts_graph_order`): reactant
@@ -159,6 +161,16 @@ int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const f
                      const tsd_interaction_t* blk, const float* h_in, float* h_out, float* ef0,
                      float* ef1, float* nf0, float* nf1, float* nf2, int32_t math,
                      tsd_stream_t stream);
+
+/* The two building blocks of K4, exposed on their own for unit tests and for the per-kernel
+ * roofline timing in bench.py:
+ *  tsd_linear          : out = act(x W^T + b) for a dense (rows, in) x; `rows_dev` (device int,
+ *                        may be NULL) overrides `rows` like the per-step edge count does.
+ *  tsd_cfconv_aggregate: agg_i = sum_{j->i} x1_j * filt_ji over the dst-sorted in-CSR. */
+int tsd_linear(int32_t rows, const int32_t* rows_dev, const float* x, const tsd_linear_t* lin, int32_t act,
+               float* out, int32_t math, tsd_stream_t stream);
+int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t channels,
+                         const float* x1, const float* filt, float* agg, tsd_stream_t stream);
 
 /* ---- K5: one GINEConv + GINEncoder glue (replaces models/encoder/gin.py:42-73,:136-143):
  *   out_i = sum_{j->i, edge local} relu(h_j + e_ji) + (1 + eps) h_i;  hid = nn1(relu(nn0(out)))

@@ -1,0 +1,108 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tsdiff_b200 import _lib as L
+from tsdiff_b200.config import AttrDict, QM9_DEFAULT_MODEL, TRAIN_CONFIG_MODEL
+from tsdiff_b200.models.epsnet import get_model
+from tsdiff_b200.synthetic import make_batch, shard_batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "tsdiff_b200.h")).read()
+    declared = set(re.findall(r"\b(tsd_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
+    if not os.path.exists(L.LIB_PATH):
+        from tsdiff_b200 import build
+        build.build()
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert L.load().tsd_version() >= 100
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """Compile the header with gcc and compare sizeof/offsetof with the ctypes mirrors."""
+    import subprocess
+    structs = {"tsd_linear_t": L.Linear, "tsd_batch_t": L.Batch, "tsd_edges_t": L.Edges,
+               "tsd_edge_encoder_t": L.EdgeEncoder, "tsd_interaction_t": L.Interaction, "tsd_gine_t": L.Gine,
+               "tsd_pair_mlp_t": L.PairMlp, "tsd_score_channel_t": L.ScoreChannel, "tsd_ld_params_t": L.LdParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tsdiff_b200.h"', 'int main(void){']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_get_model_dispatch_and_errors():
+    assert type(get_model(TRAIN_CONFIG_MODEL)).__name__ == "CondenseEncoderEpsNetwork"
+    assert type(get_model(QM9_DEFAULT_MODEL)).__name__ == "DualEncoderEpsNetwork"
+    with pytest.raises(NotImplementedError):
+        get_model(AttrDict(network="nope"))
+
+
+def test_config_access_patterns():
+    cfg = AttrDict({"a": 1, "encoder": {"name": "schnet"}})
+    assert cfg.a == 1 and cfg.get("b", 7) == 7 and cfg.get("encoder").name == "schnet"
+    assert hasattr(cfg, "a") and not hasattr(cfg, "TS")
+
+
+def test_no_cpu_fallback():
+    m = get_model(TRAIN_CONFIG_MODEL)
+    g = make_batch(1, seed=0)
+    with pytest.raises(L.TsdError):
+        m(g["atom_type"], g["r_feat"], g["p_feat"], g["pos_init"], g["bond_index"], g["bond_type"], g["batch"], None)
+    with pytest.raises(NotImplementedError):
+        m.get_loss()
+
+
+def test_checkpoint_roundtrip_strict():
+    torch.manual_seed(0)
+    a = get_model(TRAIN_CONFIG_MODEL)
+    torch.manual_seed(1)
+    b = get_model(TRAIN_CONFIG_MODEL)
+    b.load_state_dict(a.state_dict(), strict=True)  # sampling.py:130
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(v, w), k
+
+
+def test_synthetic_batch_contract():
+    g = make_batch(20, seed=1)
+    n = g["atom_type"].numel()
+    bi, bt = g["bond_index"], g["bond_type"]
+    key = bi[0] * n + bi[1]
+    assert bool((key[1:] > key[:-1]).all())  # sorted, no duplicates (datasets.py:495-498)
+    pairs = set(map(tuple, bi.t().tolist()))
+    assert all((c, r) in pairs for r, c in pairs)  # symmetric
+    assert bool((g["batch"][bi[0]] == g["batch"][bi[1]]).all())
+    assert bool((g["r_feat"].sum(1) == 8).all()) and g["r_feat"].shape == (n, 25)
+    assert 10 <= int(g["num_nodes_per_graph"].min()) and int(g["num_nodes_per_graph"].max()) <= 25
+    assert bool(((bt // 22 > 0) | (bt % 22 > 0)).all())
+
+
+def test_shards_partition_the_batch():
+    g = make_batch(10, seed=2)
+    parts = [shard_batch(g, r, 4) for r in range(4)]
+    assert sum(p["num_graphs"] for p in parts) == 10
+    assert torch.equal(torch.cat([p["atom_type"] for p in parts]), g["atom_type"])
+    off = 0
+    for p in parts:
+        assert p["atom_offset"] == off
+        off += p["atom_type"].numel()
+        assert int(p["bond_index"].min()) >= 0 and int(p["bond_index"].max()) < p["atom_type"].numel()

@@ -67,6 +67,9 @@ class LdParams(C.Structure):
 _P = C.c_void_p
 _SIGNATURES = {
     "tsd_version": [],
+    "tsd_launch_count": [],
+    "tsd_linear": [C.c_int32, _P, _P, C.POINTER(Linear), C.c_int32, _P, C.c_int32, _P],
+    "tsd_cfconv_aggregate": [C.POINTER(Batch), C.POINTER(Edges), C.c_int32, _P, _P, _P, _P],
     "tsd_last_cuda_error": [],
     "tsd_error_string": [C.c_int],
     "tsd_bond_order_build": [C.c_int, C.POINTER(Batch), C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P,
@@ -86,7 +89,7 @@ _SIGNATURES = {
     "tsd_eq_transform": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.c_float, _P, _P],
     "tsd_philox_normal": [C.c_int32, C.c_uint64, C.c_int32, C.c_int64, _P, _P],
 }
-_RESTYPES = {"tsd_error_string": C.c_char_p}
+_RESTYPES = {"tsd_error_string": C.c_char_p, "tsd_launch_count": C.c_int64}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None

@@ -12,7 +12,11 @@ int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int
                               const int* local_tab, const float* h, const float* ea, const float* eps, float* out,
                               cudaStream_t s);
 
+#include <atomic>
 static thread_local int g_last_cuda_error = 0;
+static std::atomic<long long> g_launches{0};
+void tsd_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t tsd_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int tsd_record_cuda_error(cudaError_t e) {
   g_last_cuda_error = (int)e;
@@ -210,4 +214,29 @@ extern "C" int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, 
   g.accumulate = accumulate;
   TSD_TRY(tsd_gemm(g, math, s));
   return TSD_OK;
+}
+
+extern "C" int tsd_linear(int32_t rows, const int32_t* rows_dev, const float* x, const tsd_linear_t* lin, int32_t act,
+                          float* out, int32_t math, tsd_stream_t stream) {
+  TSD_REQUIRE(x && lin && lin->weight && out && rows >= 0);
+  GemmArgs g = tsd_gemm_args();
+  g.M_cap = rows;
+  g.M_ptr = rows_dev;
+  g.N = lin->out_features;
+  g.K = lin->in_features;
+  g.W = lin->weight;
+  g.bias = lin->bias;
+  g.A = x;
+  g.lda = g.K;
+  g.C = out;
+  g.ldc = g.N;
+  g.act = act;
+  return tsd_gemm(g, math, tsd_cu(stream));
+}
+
+extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t channels,
+                                    const float* x1, const float* filt, float* agg, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && x1 && filt && agg);
+  return tsd_launch_cfconv_aggregate(batch->num_nodes, channels, edges->in_ptr, edges->in_eid, edges->row, x1, filt,
+                                     agg, tsd_cu(stream));
 }

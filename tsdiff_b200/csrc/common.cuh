@@ -16,7 +16,12 @@ int tsd_record_cuda_error(cudaError_t e);  // api.cu
     if (_e != cudaSuccess) return tsd_record_cuda_error(_e); \
   } while (0)
 
-#define TSD_LAUNCH_CHECK() TSD_CUDA(cudaGetLastError())
+void tsd_count_launch();  // api.cu
+#define TSD_LAUNCH_CHECK()         \
+  do {                             \
+    tsd_count_launch();            \
+    TSD_CUDA(cudaGetLastError());  \
+  } while (0)
 
 #define TSD_REQUIRE(cond)              \
   do {                                 \

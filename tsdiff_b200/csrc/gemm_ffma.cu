@@ -10,7 +10,7 @@ constexpr int BK = 16;
 constexpr int NTHREADS = 256;
 
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(NTHREADS) k_gemm_ffma(const GemmArgs p) {
+__global__ void __launch_bounds__(NTHREADS, 2) k_gemm_ffma(const GemmArgs p) {
   static_assert((BM / TM) * (BN / TN) == NTHREADS, "tile/thread mismatch");
   static_assert(TM == 4 || TM == 8, "TM");
   static_assert(TN == 4 || TN == 8, "TN");
