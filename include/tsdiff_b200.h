@@ -77,6 +77,7 @@ typedef struct {
   int32_t* row_ptr;    /* (N+1) out-CSR over `row` */
   int32_t* in_ptr;     /* (N+1) in-CSR: edges grouped by `col` (dst-sorted) */
   int32_t* in_eid;     /* (E) edge ids sorted by (col, row) */
+  int32_t* in_src;     /* (E) source node of in_eid[k] (= row[in_eid[k]]), saves a dependent load */
   int32_t* graph_count;/* (G) scratch: edges per graph */
 } tsd_edges_t;
 

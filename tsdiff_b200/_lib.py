@@ -30,7 +30,7 @@ class Batch(C.Structure):
 class Edges(C.Structure):
     _fields_ = [("num_edges", C.c_void_p), ("row", C.c_void_p), ("col", C.c_void_p), ("length", C.c_void_p),
                 ("tab0", C.c_void_p), ("tab1", C.c_void_p), ("in_b", C.c_void_p), ("row_ptr", C.c_void_p),
-                ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p), ("graph_count", C.c_void_p)]
+                ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p), ("in_src", C.c_void_p), ("graph_count", C.c_void_p)]
 
 
 class EdgeEncoder(C.Structure):

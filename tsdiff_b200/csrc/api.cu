@@ -148,7 +148,7 @@ extern "C" int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edg
   g.A = h_in;
   g.C = nf0;
   TSD_TRY(tsd_gemm(g, math, s));
-  TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, F, edges->in_ptr, edges->in_eid, edges->row, nf0, ef1, nf1, s));
+  TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, F, edges->in_ptr, edges->in_eid, edges->in_src, nf0, ef1, nf1, s));
   // h_out = h_in + lin(ssp(lin2(agg)))
   g = node_gemm(batch, blk->lin2);
   g.A = nf1;
@@ -170,7 +170,7 @@ extern "C" int tsd_gine_layer(const tsd_batch_t* batch, const tsd_edges_t* edges
   TSD_REQUIRE(batch && edges && edge_attr && conv && conv->eps && h_in && h_out && nf0 && nf1);
   cudaStream_t s = tsd_cu(stream);
   const int H = conv->nn0.in_features;
-  TSD_TRY(tsd_launch_gine_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->row, edges->tab0, h_in,
+  TSD_TRY(tsd_launch_gine_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, edges->tab0, h_in,
                                     edge_attr, conv->eps, nf0, s));
   GemmArgs g = node_gemm(batch, conv->nn0);
   g.A = nf0;
@@ -237,6 +237,6 @@ extern "C" int tsd_linear(int32_t rows, const int32_t* rows_dev, const float* x,
 extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t channels,
                                     const float* x1, const float* filt, float* agg, tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && x1 && filt && agg);
-  return tsd_launch_cfconv_aggregate(batch->num_nodes, channels, edges->in_ptr, edges->in_eid, edges->row, x1, filt,
+  return tsd_launch_cfconv_aggregate(batch->num_nodes, channels, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt,
                                      agg, tsd_cu(stream));
 }

@@ -22,7 +22,7 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // floats per panel row = 128 bytes = one swizzle atom row
 constexpr int TC_THREADS = 256;
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 2;
 constexpr int TC_A_PANEL_BYTES = TC_BM * TC_BK * 4;  // 16 KiB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,7 +99,26 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tf32(const GemmArgs p, int tmem_cols) {
+// fast-math activations: this arithmetic mode already carries the TF32 bound, so the SFU
+// approximations (__expf / __logf, ~2 ulp) are far below it
+template <int ACT>
+__device__ __forceinline__ float tc_act(float x) {
+  if (ACT == TSD_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == TSD_ACT_SWISH) return __fdividef(x, 1.f + __expf(-x));
+  if (ACT == TSD_ACT_SSP) return (x > 15.f ? x : __logf(1.f + __expf(x))) - TSD_SSP_SHIFT;
+  if (ACT == TSD_ACT_SOFTPLUS) return x > 15.f ? x : __logf(1.f + __expf(x));
+  return x;
+}
+
+enum { TC_EPI_PLAIN = 0, TC_EPI_SCALE = 1, TC_EPI_MULEMB = 2, TC_EPI_DOT = 3 };
+
+// Software pipeline: two shared-memory stages + one panel of register prefetch.  Iteration kb
+//   waits until the MMAs that read stage kb%2 retired, stores the prefetched panel, issues the
+//   global loads of panel kb+1 (in flight across the CTA barrier and the MMA issue), then one
+//   thread issues the 4 MMAs of panel kb.  ~98 KB smem / CTA -> two CTAs per SM hide each
+//   other's load latency; 2 x 256 TMEM columns fill the SM's 512.
+template <int ACT, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tf32(const GemmArgs p, int tmem_cols) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t bar_empty[TC_STAGES];
   __shared__ uint64_t bar_accum;
@@ -132,26 +151,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tf32(const GemmArgs p, i
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(N);
 
+  constexpr int A_LD = (TC_BM * 8) / TC_THREADS;  // 4 float4 per thread per panel
+  constexpr int B_LD = (256 * 8) / TC_THREADS;    // up to 8 (N = 256)
+  float4 ra[A_LD], rb[B_LD];
+  const int b_items = N * 8;
+  auto load_regs = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int idx = tid + i * TC_THREADS;
+      int m = m0 + (idx >> 3);
+      ra[i] = m < M ? tsd_load_a4(p, m, k0 + ((idx & 7) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      int idx = tid + i * TC_THREADS;
+      if (idx < b_items)
+        rb[i] = __ldg(reinterpret_cast<const float4*>(p.W + (size_t)(idx >> 3) * K + k0 + ((idx & 7) << 2)));
+    }
+  };
+  auto store_smem = [&](uint8_t* a_panel, uint8_t* b_panel) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int idx = tid + i * TC_THREADS;
+      *reinterpret_cast<float4*>(a_panel + sw128_off(idx >> 3, idx & 7)) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      int idx = tid + i * TC_THREADS;
+      if (idx < b_items) *reinterpret_cast<float4*>(b_panel + sw128_off(idx >> 3, idx & 7)) = rb[i];
+    }
+  };
+
   const int num_kb = K / TC_BK;
+  load_regs(0);
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % TC_STAGES, round = kb / TC_STAGES;
     if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));  // MMAs that read this stage retired
     uint8_t* a_panel = smem_gen + (size_t)s * stage_bytes;
-    uint8_t* b_panel = a_panel + TC_A_PANEL_BYTES;
-    const int k0 = kb * TC_BK;
-#pragma unroll
-    for (int i = 0; i < (TC_BM * 8) / TC_THREADS; ++i) {
-      int idx = tid + i * TC_THREADS;
-      int r = idx >> 3, c = idx & 7;
-      int m = m0 + r;
-      float4 v = m < M ? tsd_load_a4(p, m, k0 + (c << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(a_panel + sw128_off(r, c)) = v;
-    }
-    for (int idx = tid; idx < N * 8; idx += TC_THREADS) {
-      int r = idx >> 3, c = idx & 7;
-      float4 v = __ldg(reinterpret_cast<const float4*>(p.W + (size_t)r * K + k0 + (c << 2)));
-      *reinterpret_cast<float4*>(b_panel + sw128_off(r, c)) = v;
-    }
+    store_smem(a_panel, a_panel + TC_A_PANEL_BYTES);
+    if (kb + 1 < num_kb) load_regs((kb + 1) * TC_BK);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
     __syncthreads();
     if (tid == 0) {
@@ -174,32 +212,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tf32(const GemmArgs p, i
   const bool live = m < M;
   const int cols_per_half = N >> 1;
   float cscale = 1.f;
-  if (live && p.scale_len) cscale = tsd_cutoff_fn(p.scale_len[m], p.cutoff, p.smooth);
+  if (EPI == TC_EPI_SCALE && live) cscale = tsd_cutoff_fn(p.scale_len[m], p.cutoff, p.smooth);
+  const float* emb_row = nullptr;
+  if (EPI == TC_EPI_MULEMB && live) emb_row = p.mul_emb + (size_t)(p.mul_code[m] & 0xffff) * N;
+  const float* res_row = (EPI == TC_EPI_PLAIN && p.residual && live) ? p.residual + (size_t)m * p.ldr : nullptr;
   float dot = 0.f;
   for (int cc = 0; cc < cols_per_half; cc += 32) {
     const int c0 = half * cols_per_half + cc;
     uint32_t v[32];
     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-    if (p.out_vec) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = live ? tsd_epilogue(p, m, c0 + j, __uint_as_float(v[j]), cscale) : 0.f;
-        dot = fmaf(x, p.w3[c0 + j], dot);
-      }
-    } else if (live) {
-      float* dst = p.C + (size_t)m * p.ldc + c0;
+    if (live) {
+      float* dst = (EPI == TC_EPI_DOT) ? nullptr : p.C + (size_t)m * p.ldc + c0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
+        float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 o;
-        o.x = tsd_epilogue(p, m, c0 + j + 0, __uint_as_float(v[j + 0]), cscale);
-        o.y = tsd_epilogue(p, m, c0 + j + 1, __uint_as_float(v[j + 1]), cscale);
-        o.z = tsd_epilogue(p, m, c0 + j + 2, __uint_as_float(v[j + 2]), cscale);
-        o.w = tsd_epilogue(p, m, c0 + j + 3, __uint_as_float(v[j + 3]), cscale);
-        *reinterpret_cast<float4*>(dst + j) = o;
+        o.x = tc_act<ACT>(__uint_as_float(v[j + 0]) + b.x);
+        o.y = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
+        o.z = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
+        o.w = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+        if (EPI == TC_EPI_SCALE) {
+          o.x *= cscale; o.y *= cscale; o.z *= cscale; o.w *= cscale;
+        }
+        if (EPI == TC_EPI_MULEMB) {
+          float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + c0 + j));
+          o.x *= e.x; o.y *= e.y; o.z *= e.z; o.w *= e.w;
+        }
+        if (EPI == TC_EPI_PLAIN && res_row) {
+          float4 r = *reinterpret_cast<const float4*>(res_row + c0 + j);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (EPI == TC_EPI_DOT) {
+          float4 w = __ldg(reinterpret_cast<const float4*>(p.w3 + c0 + j));
+          dot = fmaf(o.x, w.x, dot); dot = fmaf(o.y, w.y, dot); dot = fmaf(o.z, w.z, dot); dot = fmaf(o.w, w.w, dot);
+        } else {
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
       }
     }
   }
-  if (p.out_vec) {
+  if (EPI == TC_EPI_DOT) {
     if (half == 1) s_dot[row] = dot;
     __syncthreads();
     if (half == 0 && live) {
@@ -215,21 +267,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tf32(const GemmArgs p, i
   }
 }
 
+template <int ACT, int EPI>
+int tc_launch(const GemmArgs& g, int tmem_cols, size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  k_gemm_tf32<ACT, EPI><<<tsd_ceil_div(g.M_cap, TC_BM), TC_THREADS, smem, stream>>>(g, tmem_cols);
+  TSD_LAUNCH_CHECK();
+  return TSD_OK;
+}
+
+template <int EPI>
+int tc_dispatch_act(const GemmArgs& g, int tmem_cols, size_t smem, cudaStream_t stream) {
+  switch (g.act) {
+    case TSD_ACT_NONE: return tc_launch<TSD_ACT_NONE, EPI>(g, tmem_cols, smem, stream);
+    case TSD_ACT_RELU: return tc_launch<TSD_ACT_RELU, EPI>(g, tmem_cols, smem, stream);
+    case TSD_ACT_SWISH: return tc_launch<TSD_ACT_SWISH, EPI>(g, tmem_cols, smem, stream);
+    case TSD_ACT_SSP: return tc_launch<TSD_ACT_SSP, EPI>(g, tmem_cols, smem, stream);
+    default: return TSD_ERR_UNSUPPORTED;
+  }
+}
+
 }  // namespace
 
 int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream) {
   // shapes outside the tensor-core kernel's envelope go back to the FFMA kernel (tsd_gemm)
   if (!(g.N == 64 || g.N == 128 || g.N == 256) || g.K % TC_BK != 0 || g.K <= 0) return TSD_ERR_UNSUPPORTED;
-  if (g.M_cap < 4096) return TSD_ERR_UNSUPPORTED;  // node-level GEMMs: too few 128-row tiles to fill 148 SMs
+  if (g.M_cap < 1024) return TSD_ERR_UNSUPPORTED;
   TSD_REQUIRE(g.W && (g.a_kind == TSD_A_EDGE_MLP0 || g.A) && (g.out_vec || g.C));
   const int tmem_cols = g.N < 32 ? 32 : g.N;  // power of two >= 32
   const size_t smem = (size_t)TC_STAGES * (TC_A_PANEL_BYTES + (size_t)g.N * TC_BK * 4) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  k_gemm_tf32<<<tsd_ceil_div(g.M_cap, TC_BM), TC_THREADS, smem, stream>>>(g, tmem_cols);
-  TSD_LAUNCH_CHECK();
-  return TSD_OK;
+  const int n_epi = (g.scale_len != nullptr) + (g.mul_emb != nullptr) + (g.out_vec != nullptr);
+  if (n_epi > 1 || (n_epi == 1 && g.residual)) return TSD_ERR_UNSUPPORTED;
+  if (g.out_vec) return tc_dispatch_act<TC_EPI_DOT>(g, tmem_cols, smem, stream);
+  if (g.scale_len) return tc_dispatch_act<TC_EPI_SCALE>(g, tmem_cols, smem, stream);
+  if (g.mul_emb) return tc_dispatch_act<TC_EPI_MULEMB>(g, tmem_cols, smem, stream);
+  return tc_dispatch_act<TC_EPI_PLAIN>(g, tmem_cols, smem, stream);
 }

@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(256) k_edge_emit(tsd_batch_t b, const float* _
         for (int w2 = 0; w2 < (c >> 5); ++w2) rank += __popc(orow[w2]);
         rank += __popc(orow[c >> 5] & ((1u << (c & 31)) - 1u));
         e.in_eid[k] = gbase + row_off[r] + rank;
+        e.in_src[k] = t.n0 + r;
       }
       running += __popc(bits);
     }
@@ -359,7 +360,7 @@ extern "C" int tsd_edge_build(const tsd_batch_t* batch, const float* pos, double
                               const tsd_edges_t* edges, tsd_stream_t stream) {
   TSD_REQUIRE(batch && pos && table0 && edges);
   TSD_REQUIRE(edges->num_edges && edges->row && edges->col && edges->length && edges->tab0 && edges->row_ptr &&
-              edges->in_ptr && edges->in_eid && edges->graph_count);
+              edges->in_ptr && edges->in_eid && edges->in_src && edges->graph_count);
   TSD_REQUIRE(batch->max_graph_nodes >= 1 && batch->max_graph_nodes <= TSD_MAX_GRAPH_NODES);
   TSD_REQUIRE(!tab1_is_graph || table1);
   if (batch->num_graphs == 0) return TSD_OK;

@@ -126,9 +126,57 @@ extern "C" int tsd_eq_transform(const tsd_batch_t* batch, const tsd_edges_t* edg
 }
 
 // ------------------------------------------------------------------------------------- K7
+// Per-edge terms t_e = ((1/len_e) (p_row - p_col)) * s_e are computed ONCE per edge by all the
+// threads (coalesced loads) into shared memory; every atom then adds its out-edge terms and
+// subtracts its in-edge terms sequentially in edge order -- the same association order (and
+// the same bits) as the per-atom global-memory walk of tsd_node_score, without its chain of
+// dependent global loads.  Edges masked out of a channel contribute an exact +0.
+struct LdSmem {
+  float* term0;   // [cap][3]
+  float* term1;   // [cap][3] (two-channel variant)
+  int* in_local;  // [cap] in-slot -> edge id local to the graph
+};
+
+__device__ __forceinline__ void k7_edge_terms(const tsd_score_channel_t& ch, const tsd_edges_t& e, const float* spos,
+                                              int n0, int e0, int count, float inv_div, float* term) {
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    const int id = e0 + k;
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (tsd_edge_selected(ch, id)) {
+      const int r = e.row[id] - n0, c = e.col[id] - n0;
+      const float inv_len = __fdiv_rn(1.0f, e.length[id]);
+      const float s = __fdiv_rn(ch.inv[id], inv_div);
+      tx = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r], spos[3 * c])), s);
+      ty = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 1], spos[3 * c + 1])), s);
+      tz = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 2], spos[3 * c + 2])), s);
+    }
+    term[3 * k] = tx;
+    term[3 * k + 1] = ty;
+    term[3 * k + 2] = tz;
+  }
+}
+
+__device__ __forceinline__ float3 k7_node_sum(const tsd_edges_t& e, const float* term, const int* in_local, int e0,
+                                              int i) {
+  float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+  for (int k = e.row_ptr[i] - e0, end = e.row_ptr[i + 1] - e0; k < end; ++k) {
+    ax = __fadd_rn(ax, term[3 * k]);
+    ay = __fadd_rn(ay, term[3 * k + 1]);
+    az = __fadd_rn(az, term[3 * k + 2]);
+  }
+  for (int k = e.in_ptr[i] - e0, end = e.in_ptr[i + 1] - e0; k < end; ++k) {
+    const int id = in_local[k];
+    bx = __fadd_rn(bx, -term[3 * id]);
+    by = __fadd_rn(by, -term[3 * id + 1]);
+    bz = __fadd_rn(bz, -term[3 * id + 2]);
+  }
+  return make_float3(__fadd_rn(ax, bx), __fadd_rn(ay, by), __fadd_rn(az, bz));
+}
+
 __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, tsd_edges_t e, float* __restrict__ pos,
                                                                 tsd_score_channel_t ch0, tsd_score_channel_t ch1,
-                                                                tsd_ld_params_t ld) {
+                                                                tsd_ld_params_t ld, int smem_edge_cap) {
+  extern __shared__ float k7_dyn[];
   __shared__ float spos[3 * TSD_MAX_GRAPH_NODES];
   __shared__ float snew[3 * TSD_MAX_GRAPH_NODES];
   __shared__ float smean[3];
@@ -142,11 +190,25 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
   if (step < ld.num_steps) {
     const float step_size = ld.sched[4 * step], sigma = ld.sched[4 * step + 1], nscale = ld.sched[4 * step + 2];
     const bool use1 = ch1.inv != nullptr && ld.sched[4 * step + 3] != 0.f;
+    const int e0 = e.row_ptr[n0], count = e.row_ptr[n0 + n] - e0;  // this graph's edges are contiguous
+    const bool staged = count <= smem_edge_cap;
+    LdSmem sm;
+    sm.term0 = k7_dyn;
+    sm.term1 = k7_dyn + 3 * (size_t)smem_edge_cap;
+    sm.in_local = reinterpret_cast<int*>(k7_dyn + (ch1.inv ? 6 : 3) * (size_t)smem_edge_cap);
+    if (staged) {
+      k7_edge_terms(ch0, e, spos, n0, e0, count, ld.inv_div, sm.term0);
+      if (use1) k7_edge_terms(ch1, e, spos, n0, e0, count, ld.inv_div, sm.term1);
+      for (int k = threadIdx.x; k < count; k += blockDim.x) sm.in_local[k] = e.in_eid[e0 + k] - e0;
+      __syncthreads();
+    }
     for (int li = threadIdx.x; li < n; li += blockDim.x) {
       const int i = n0 + li;
-      float3 eps = tsd_clip_norm(tsd_node_score(ch0, e, spos, n0, i, ld.inv_div), ch0.clip);
+      float3 eps = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, i) : tsd_node_score(ch0, e, spos, n0, i, ld.inv_div);
+      eps = tsd_clip_norm(eps, ch0.clip);
       if (use1) {
-        float3 g1 = tsd_clip_norm(tsd_node_score(ch1, e, spos, n0, i, ld.inv_div), ch1.clip);
+        float3 g1 = staged ? k7_node_sum(e, sm.term1, sm.in_local, e0, i) : tsd_node_score(ch1, e, spos, n0, i, ld.inv_div);
+        g1 = tsd_clip_norm(g1, ch1.clip);
         eps.x = __fadd_rn(eps.x, __fmul_rn(g1.x, ch1.weight));
         eps.y = __fadd_rn(eps.y, __fmul_rn(g1.y, ch1.weight));
         eps.z = __fadd_rn(eps.z, __fmul_rn(g1.z, ch1.weight));
@@ -206,8 +268,19 @@ extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, f
   tsd_score_channel_t off;
   memset(&off, 0, sizeof(off));
   int threads = ((batch->max_graph_nodes + 31) / 32) * 32;
-  if (threads < 32) threads = 32;
-  k_ld_step<<<batch->num_graphs, threads, 0, tsd_cu(stream)>>>(*batch, *edges, pos, *ch0, ch1 ? *ch1 : off, *ld);
+  if (threads < 128) threads = 128;  // extra warps only help the per-edge staging loops
+  // stage the per-edge terms of one graph in shared memory when they fit (<= 160 KB)
+  const int nch = (ch1 && ch1->inv) ? 2 : 1;
+  const long long max_edges = (long long)batch->max_graph_nodes * (batch->max_graph_nodes - 1);
+  const long long bytes = max_edges * (12 * nch + 4);
+  int cap = 0;
+  size_t smem = 0;
+  if (max_edges > 0 && bytes <= 160 * 1024) {
+    cap = (int)max_edges;
+    smem = (size_t)bytes;
+    if (smem > 40 * 1024) TSD_CUDA(cudaFuncSetAttribute(k_ld_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  }
+  k_ld_step<<<batch->num_graphs, threads, smem, tsd_cu(stream)>>>(*batch, *edges, pos, *ch0, ch1 ? *ch1 : off, *ld, cap);
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }

@@ -8,103 +8,129 @@
 #include "common.cuh"
 
 // HBM-bound: per target node stream its in-edges' filter rows (E*H*4 bytes in total, each
-// read exactly once, 16 B per lane, fully coalesced 4*LPN-byte rows) and gather x1 rows
+// read exactly once, 16 B per lane, fully coalesced 512-byte slabs) and gather x1 rows
 // (N*H*4 bytes, L2 resident).  Algorithmic bytes: E*H*4 + 2*N*H*4 + E*8 + (N+1)*4.
-template <int UNROLL>
-__global__ void __launch_bounds__(256) k_cfconv_aggregate(int num_nodes, int H, const int* __restrict__ in_ptr,
-                                                          const int* __restrict__ in_eid,
-                                                          const int* __restrict__ row, const float* __restrict__ x1,
-                                                          const float* __restrict__ filt, float* __restrict__ agg) {
-  const int lpn = H >> 2;  // lanes per node, one float4 each
-  const int npb = blockDim.x / lpn;
-  const int node = blockIdx.x * npb + threadIdx.x / lpn;
-  const int lane = threadIdx.x % lpn;
-  if (node >= num_nodes || threadIdx.x >= npb * lpn) return;
-  const int beg = in_ptr[node], end = in_ptr[node + 1];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int k = beg;
-  for (; k + UNROLL <= end; k += UNROLL) {
-    int e[UNROLL], r[UNROLL];
-    float4 w[UNROLL], x[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) e[u] = in_eid[k + u];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) r[u] = row[e[u]];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      w[u] = __ldcs(reinterpret_cast<const float4*>(filt + (size_t)e[u] * H) + lane);  // streamed once
-      x[u] = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)r[u] * H) + lane);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      acc.x = __fadd_rn(acc.x, __fmul_rn(x[u].x, w[u].x));
-      acc.y = __fadd_rn(acc.y, __fmul_rn(x[u].y, w[u].y));
-      acc.z = __fadd_rn(acc.z, __fmul_rn(x[u].z, w[u].z));
-      acc.w = __fadd_rn(acc.w, __fmul_rn(x[u].w, w[u].w));
-    }
-  }
-  for (; k < end; ++k) {
-    int e = in_eid[k];
-    int r = row[e];
-    float4 w = __ldcs(reinterpret_cast<const float4*>(filt + (size_t)e * H) + lane);
-    float4 x = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)r * H) + lane);
-    acc.x = __fadd_rn(acc.x, __fmul_rn(x.x, w.x));
-    acc.y = __fadd_rn(acc.y, __fmul_rn(x.y, w.y));
-    acc.z = __fadd_rn(acc.z, __fmul_rn(x.z, w.z));
-    acc.w = __fadd_rn(acc.w, __fmul_rn(x.w, w.w));
-  }
-  reinterpret_cast<float4*>(agg + (size_t)node * H)[lane] = acc;
+// One warp per (target node, 128-channel slab).  The lanes first fetch the segment's edge
+// ids and source ids coalesced, then broadcast them with shuffles, so the row loads of
+// consecutive edges are independent and UNROLL of them are in flight per lane.
+__device__ __forceinline__ void tsd_fma_rn4(float4& acc, const float4& x, const float4& w) {
+  acc.x = __fadd_rn(acc.x, __fmul_rn(x.x, w.x));
+  acc.y = __fadd_rn(acc.y, __fmul_rn(x.y, w.y));
+  acc.z = __fadd_rn(acc.z, __fmul_rn(x.z, w.z));
+  acc.w = __fadd_rn(acc.w, __fmul_rn(x.w, w.w));
 }
 
-int tsd_launch_cfconv_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_cfconv_aggregate(int num_nodes, int H, int slabs,
+                                                          const int* __restrict__ in_ptr,
+                                                          const int* __restrict__ in_eid,
+                                                          const int* __restrict__ in_src, const float* __restrict__ x1,
+                                                          const float* __restrict__ filt, float* __restrict__ agg) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int node = gw / slabs, slab = gw - node * slabs;
+  if (node >= num_nodes) return;  // warp uniform
+  const int off = slab * 128 + lane * 4;
+  const bool active = off < H;
+  const int beg = in_ptr[node], end = in_ptr[node + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    const int e_l = lane < cnt ? in_eid[base + lane] : 0;
+    const int r_l = lane < cnt ? in_src[base + lane] : 0;
+    int j = 0;
+    for (; j + UNROLL <= cnt; j += UNROLL) {
+      float4 w[UNROLL], x[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int e = __shfl_sync(TSD_FULL_MASK, e_l, j + u), r = __shfl_sync(TSD_FULL_MASK, r_l, j + u);
+        if (active) {
+          w[u] = __ldcs(reinterpret_cast<const float4*>(filt + (size_t)e * H + off));  // streamed once
+          x[u] = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)r * H + off));
+        }
+      }
+      if (active) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) tsd_fma_rn4(acc, x[u], w[u]);
+      }
+    }
+    for (; j < cnt; ++j) {
+      const int e = __shfl_sync(TSD_FULL_MASK, e_l, j), r = __shfl_sync(TSD_FULL_MASK, r_l, j);
+      if (active) {
+        float4 w = __ldcs(reinterpret_cast<const float4*>(filt + (size_t)e * H + off));
+        float4 x = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)r * H + off));
+        tsd_fma_rn4(acc, x, w);
+      }
+    }
+  }
+  if (active) *reinterpret_cast<float4*>(agg + (size_t)node * H + off) = acc;
+}
+
+int tsd_launch_cfconv_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* in_src,
                                 const float* x1, const float* filt, float* agg, cudaStream_t s) {
-  TSD_REQUIRE(H % 4 == 0 && H >= 4 && H <= 1024);
+  TSD_REQUIRE(H % 4 == 0 && H >= 4 && H <= 4096);
   if (num_nodes == 0) return TSD_OK;
-  int lpn = H / 4, npb = 256 / lpn;
-  k_cfconv_aggregate<4><<<tsd_ceil_div(num_nodes, npb), 256, 0, s>>>(num_nodes, H, in_ptr, in_eid, row, x1, filt, agg);
+  const int slabs = tsd_ceil_div(H, 128);
+  const long long warps = (long long)num_nodes * slabs;
+  k_cfconv_aggregate<8><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1,
+                                                                    filt, agg);
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }
 
-__global__ void __launch_bounds__(256) k_gine_aggregate(int num_nodes, int H, const int* __restrict__ in_ptr,
-                                                        const int* __restrict__ in_eid, const int* __restrict__ row,
+__global__ void __launch_bounds__(256) k_gine_aggregate(int num_nodes, int H, int slabs,
+                                                        const int* __restrict__ in_ptr,
+                                                        const int* __restrict__ in_eid, const int* __restrict__ in_src,
                                                         const int* __restrict__ local_tab,
                                                         const float* __restrict__ h, const float* __restrict__ ea,
                                                         const float* __restrict__ eps, float* __restrict__ out) {
-  const int lpn = H >> 2;
-  const int npb = blockDim.x / lpn;
-  const int node = blockIdx.x * npb + threadIdx.x / lpn;
-  const int lane = threadIdx.x % lpn;
-  if (node >= num_nodes || threadIdx.x >= npb * lpn) return;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int node = gw / slabs, slab = gw - node * slabs;
+  if (node >= num_nodes) return;
+  const int off = slab * 128 + lane * 4;
+  const bool active = off < H;
   const int beg = in_ptr[node], end = in_ptr[node + 1];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = beg; k < end; ++k) {
-    int e = in_eid[k];
-    if (local_tab[e] == 0) continue;  // GIN runs on edge_index[:, edge_type > 0] (dualenc.py:343-347)
-    int r = row[e];
-    float4 a = __ldg(reinterpret_cast<const float4*>(ea + (size_t)e * H) + lane);
-    float4 x = __ldg(reinterpret_cast<const float4*>(h + (size_t)r * H) + lane);
-    acc.x = __fadd_rn(acc.x, fmaxf(__fadd_rn(x.x, a.x), 0.f));
-    acc.y = __fadd_rn(acc.y, fmaxf(__fadd_rn(x.y, a.y), 0.f));
-    acc.z = __fadd_rn(acc.z, fmaxf(__fadd_rn(x.z, a.z), 0.f));
-    acc.w = __fadd_rn(acc.w, fmaxf(__fadd_rn(x.w, a.w), 0.f));
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    int e_l = 0, r_l = 0, loc_l = 0;
+    if (lane < cnt) {
+      e_l = in_eid[base + lane];
+      r_l = in_src[base + lane];
+      loc_l = local_tab[e_l];  // GIN runs on edge_index[:, edge_type > 0] (dualenc.py:343-347)
+    }
+    for (int j = 0; j < cnt; ++j) {
+      const int e = __shfl_sync(TSD_FULL_MASK, e_l, j), r = __shfl_sync(TSD_FULL_MASK, r_l, j);
+      const int loc = __shfl_sync(TSD_FULL_MASK, loc_l, j);
+      if (loc != 0 && active) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(ea + (size_t)e * H + off));
+        float4 x = __ldg(reinterpret_cast<const float4*>(h + (size_t)r * H + off));
+        acc.x = __fadd_rn(acc.x, fmaxf(__fadd_rn(x.x, a.x), 0.f));
+        acc.y = __fadd_rn(acc.y, fmaxf(__fadd_rn(x.y, a.y), 0.f));
+        acc.z = __fadd_rn(acc.z, fmaxf(__fadd_rn(x.z, a.z), 0.f));
+        acc.w = __fadd_rn(acc.w, fmaxf(__fadd_rn(x.w, a.w), 0.f));
+      }
+    }
   }
-  const float s = __fadd_rn(1.f, eps[0]);
-  float4 x = reinterpret_cast<const float4*>(h + (size_t)node * H)[lane];
-  acc.x = __fadd_rn(acc.x, __fmul_rn(s, x.x));
-  acc.y = __fadd_rn(acc.y, __fmul_rn(s, x.y));
-  acc.z = __fadd_rn(acc.z, __fmul_rn(s, x.z));
-  acc.w = __fadd_rn(acc.w, __fmul_rn(s, x.w));
-  reinterpret_cast<float4*>(out + (size_t)node * H)[lane] = acc;
+  if (active) {
+    const float s = __fadd_rn(1.f, eps[0]);
+    float4 x = *reinterpret_cast<const float4*>(h + (size_t)node * H + off);
+    acc.x = __fadd_rn(acc.x, __fmul_rn(s, x.x));
+    acc.y = __fadd_rn(acc.y, __fmul_rn(s, x.y));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(s, x.z));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(s, x.w));
+    *reinterpret_cast<float4*>(out + (size_t)node * H + off) = acc;
+  }
 }
 
-int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
+int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* in_src,
                               const int* local_tab, const float* h, const float* ea, const float* eps, float* out,
                               cudaStream_t s) {
-  TSD_REQUIRE(H % 4 == 0 && H >= 4 && H <= 1024);
+  TSD_REQUIRE(H % 4 == 0 && H >= 4 && H <= 4096);
   if (num_nodes == 0) return TSD_OK;
-  int lpn = H / 4, npb = 256 / lpn;
-  k_gine_aggregate<<<tsd_ceil_div(num_nodes, npb), 256, 0, s>>>(num_nodes, H, in_ptr, in_eid, row, local_tab, h, ea, eps, out);
+  const int slabs = tsd_ceil_div(H, 128);
+  const long long warps = (long long)num_nodes * slabs;
+  k_gine_aggregate<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, local_tab,
+                                                                h, ea, eps, out);
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }

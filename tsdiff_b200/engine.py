@@ -89,10 +89,11 @@ class BatchPlan:
         self.row_ptr = torch.zeros(n + 1, **i32)
         self.in_ptr = torch.zeros(n + 1, **i32)
         self.in_eid = torch.zeros(cap, **i32)
+        self.in_src = torch.zeros(cap, **i32)
         self.graph_count = torch.zeros(max(g, 1), **i32)
         self.c_edges = L.Edges(*[t.data_ptr() for t in (
             self.num_edges, self.row, self.col, self.length, self.tab0, self.tab1, self.in_b, self.row_ptr,
-            self.in_ptr, self.in_eid, self.graph_count)])
+            self.in_ptr, self.in_eid, self.in_src, self.graph_count)])
 
     def build_edges(self, pos, cutoff, max_neighbors=32):
         """K2: refill the edge list for the current positions (no sync)."""
