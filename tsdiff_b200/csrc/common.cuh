@@ -35,8 +35,11 @@ static inline int tsd_ceil_div(int a, int b) { return (a + b - 1) / b; }
 #define TSD_SSP_SHIFT 0.693147182464599609375f
 
 __device__ __forceinline__ float tsd_softplus(float x) {
-  // F.softplus(beta=1, threshold=20)
-  return x > 20.f ? x : log1pf(expf(x));
+  // F.softplus(beta=1, threshold=20) in the branch-free stable form max(x,0) + log1p(exp(-|x|)):
+  // identical to log1p(exp(x)) up to rounding, returns x exactly for x > 20 (the correction is
+  // < 2^-29 x), and -- unlike `x > 20 ? x : ...` -- compiles without a per-element branch, so
+  // the unrolled epilogues keep their instruction-level parallelism.
+  return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
 }
 
 __device__ __forceinline__ float tsd_act(int act, float x) {
@@ -47,6 +50,16 @@ __device__ __forceinline__ float tsd_act(int act, float x) {
     case TSD_ACT_SOFTPLUS: return tsd_softplus(x);
     default: return x;
   }
+}
+
+// compile-time selected activation (accurate math): keeps unrolled epilogues small
+template <int ACT>
+__device__ __forceinline__ float tsd_act_t(float x) {
+  if (ACT == TSD_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == TSD_ACT_SWISH) return x * (1.f / (1.f + expf(-x)));
+  if (ACT == TSD_ACT_SSP) return tsd_softplus(x) - TSD_SSP_SHIFT;
+  if (ACT == TSD_ACT_SOFTPLUS) return tsd_softplus(x);
+  return x;
 }
 
 // Canonical fp32 squared distance: (dx*dx + dy*dy) + dz*dz, every op rounded (no FMA

@@ -8,10 +8,16 @@
 //   A_PAIR      : k < H ? h[row[m], k] * h[col[m], k] : ea[m, k-H]     (common.py:226-229)
 // The number of rows is read from device memory (M_ptr) so one captured launch serves any
 // per-step edge count up to M_cap.
+//
+// Code-size note: the kernels are specialised at compile time on the activation, the
+// epilogue flavour and (tensor-core kernel) the A kind.  A first version selected them at
+// run time inside fully unrolled loops and grew to 10-16k SASS instructions per kernel,
+// which made every launch instruction-cache bound (ncu: stall_no_inst).
 #pragma once
 #include "common.cuh"
 
 enum { TSD_A_PLAIN = 0, TSD_A_EDGE_MLP0 = 1, TSD_A_CAT = 2, TSD_A_PAIR = 3 };
+enum { TSD_EPI_PLAIN = 0, TSD_EPI_SCALE = 1, TSD_EPI_MULEMB = 2, TSD_EPI_DOT = 3 };
 
 struct GemmArgs {
   int M_cap;
@@ -32,19 +38,20 @@ struct GemmArgs {
   const float* W;
   const float* bias;
   int act;
-  const float* scale_len;  // epilogue: *= C(len[m]) (cutoff envelope)
+  const float* scale_len;  // EPI_SCALE: *= C(len[m]) (cutoff envelope)
   float cutoff;
   int smooth;
-  const float* mul_emb;    // epilogue: *= mul_emb[(mul_code[m] & 0xffff) * N + n]
+  const float* mul_emb;    // EPI_MULEMB: *= mul_emb[(mul_code[m] & 0xffff) * N + n]
   const int* mul_code;
-  const float* residual;   // epilogue: += residual[m * ldr + n]
+  const float* residual;   // EPI_PLAIN only: += residual[m * ldr + n]
   int ldr;
   float* C;
   int ldc;
-  const float* w3;         // final-dot epilogue: out_vec[m] (+)= sum_n v[m,n] * w3[n] + b3
+  const float* w3;         // EPI_DOT: out_vec[m] (+)= sum_n v[m,n] * w3[n] + b3
   const float* b3;
   float* out_vec;
   int accumulate;
+  unsigned long long* dbg;  // optional timeline buffer (TSD_GEMM_DBG=1), CTA 0 writes globaltimer stamps
 };
 
 static inline GemmArgs tsd_gemm_args() {
@@ -53,49 +60,65 @@ static inline GemmArgs tsd_gemm_args() {
   return g;
 }
 
-// 4 consecutive k of the A operand of row m (m < M, k % 4 == 0)
-__device__ __forceinline__ float4 tsd_load_a4(const GemmArgs& p, int m, int k) {
-  switch (p.a_kind) {
-    case TSD_A_EDGE_MLP0: {
-      float l = p.len[m];
-      float4 w = *reinterpret_cast<const float4*>(p.w0 + k);
-      float4 b = *reinterpret_cast<const float4*>(p.b0 + k);
-      return make_float4(tsd_act(p.act0, fmaf(l, w.x, b.x)), tsd_act(p.act0, fmaf(l, w.y, b.y)),
-                         tsd_act(p.act0, fmaf(l, w.z, b.z)), tsd_act(p.act0, fmaf(l, w.w, b.w)));
-    }
-    case TSD_A_CAT: {
-      int code = p.code[m];
-      int hi = k >= p.H;
-      int kk = k - (hi ? p.H : 0);
-      int r = hi ? ((unsigned)code >> 16) : (code & 0xffff);
-      float4 d = *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + kk);
-      float4 e = *reinterpret_cast<const float4*>(p.emb + (size_t)r * p.H + kk);
-      return make_float4(d.x * e.x, d.y * e.y, d.z * e.z, d.w * e.w);
-    }
-    case TSD_A_PAIR: {
-      if (k < p.H) {
-        float4 a = *reinterpret_cast<const float4*>(p.h + (size_t)p.row[m] * p.H + k);
-        float4 b = *reinterpret_cast<const float4*>(p.h + (size_t)p.col[m] * p.H + k);
-        return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
-      }
-      return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + (k - p.H));
-    }
-    default:
-      return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);
-  }
+// which epilogue flavour a call needs; -1 if the combination is not expressible
+static inline int tsd_gemm_epi_kind(const GemmArgs& g) {
+  const int n = (g.scale_len != nullptr) + (g.mul_emb != nullptr) + (g.out_vec != nullptr);
+  if (n > 1 || (n == 1 && g.residual)) return -1;
+  if (g.out_vec) return TSD_EPI_DOT;
+  if (g.scale_len) return TSD_EPI_SCALE;
+  if (g.mul_emb) return TSD_EPI_MULEMB;
+  return TSD_EPI_PLAIN;
 }
 
-// element (m, n) of the epilogue given the raw accumulator
-__device__ __forceinline__ float tsd_epilogue(const GemmArgs& p, int m, int n, float acc, float cscale) {
-  float v = acc;
-  if (p.bias) v += p.bias[n];
-  v = tsd_act(p.act, v);
-  if (p.scale_len) v *= cscale;
-  if (p.mul_emb) v *= p.mul_emb[(size_t)(p.mul_code[m] & 0xffff) * p.N + n];
-  if (p.residual) v += p.residual[(size_t)m * p.ldr + n];
+// run-time selected activation on 4 values; deliberately NOT inlined so the prologue of the
+// edge-MLP layer 0 (the only place that needs a run-time activation) costs one copy of the code
+static __device__ __noinline__ float4 tsd_act4_rt(int act, float4 v) {
+  v.x = tsd_act(act, v.x);
+  v.y = tsd_act(act, v.y);
+  v.z = tsd_act(act, v.z);
+  v.w = tsd_act(act, v.w);
   return v;
 }
 
-int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream);        // dispatch
+// 4 consecutive k of the A operand of row m (m < M, k % 4 == 0), A kind known at compile time
+template <int AKIND>
+__device__ __forceinline__ float4 tsd_load_a4_t(const GemmArgs& p, int m, int k) {
+  if (AKIND == TSD_A_EDGE_MLP0) {
+    const float l = p.len[m];
+    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w0 + k));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.b0 + k));
+    return tsd_act4_rt(p.act0, make_float4(fmaf(l, w.x, b.x), fmaf(l, w.y, b.y), fmaf(l, w.z, b.z), fmaf(l, w.w, b.w)));
+  }
+  if (AKIND == TSD_A_CAT) {
+    const int code = p.code[m];
+    const int hi = k >= p.H;
+    const int kk = k - (hi ? p.H : 0);
+    const int r = hi ? ((unsigned)code >> 16) : (code & 0xffff);
+    const float4 d = *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + kk);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)r * p.H + kk));
+    return make_float4(d.x * e.x, d.y * e.y, d.z * e.z, d.w * e.w);
+  }
+  if (AKIND == TSD_A_PAIR) {
+    if (k < p.H) {
+      const float4 a = *reinterpret_cast<const float4*>(p.h + (size_t)p.row[m] * p.H + k);
+      const float4 b = *reinterpret_cast<const float4*>(p.h + (size_t)p.col[m] * p.H + k);
+      return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+    }
+    return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + (k - p.H));
+  }
+  return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);
+}
+
+// run-time A kind (FFMA kernel: one uniform branch per 16-byte load)
+__device__ __forceinline__ float4 tsd_load_a4(const GemmArgs& p, int m, int k) {
+  switch (p.a_kind) {
+    case TSD_A_EDGE_MLP0: return tsd_load_a4_t<TSD_A_EDGE_MLP0>(p, m, k);
+    case TSD_A_CAT: return tsd_load_a4_t<TSD_A_CAT>(p, m, k);
+    case TSD_A_PAIR: return tsd_load_a4_t<TSD_A_PAIR>(p, m, k);
+    default: return tsd_load_a4_t<TSD_A_PLAIN>(p, m, k);
+  }
+}
+
+int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream);        // dispatch (api.cu)
 int tsd_gemm_ffma(const GemmArgs& g, cudaStream_t stream);             // gemm_ffma.cu
 int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream);             // gemm_tc.cu

@@ -1,7 +1,8 @@
 // FP32 FFMA realisation of the fused linear-layer GEMM (gemm.cuh): the strict-parity path
 // (north_star: "plain FFMA wherever tolerance demands it").  Classic shared-memory tiled
 // SGEMM, register-staged double buffering, 256 threads, BK = 16; thread tiles are split in
-// two half-tile groups so shared-memory float4 reads are conflict free.
+// two half-tile groups so shared-memory float4 reads are conflict free.  Activation and
+// epilogue flavour are template parameters (see the code-size note in gemm.cuh).
 #include "gemm.cuh"
 
 namespace {
@@ -9,7 +10,7 @@ namespace {
 constexpr int BK = 16;
 constexpr int NTHREADS = 256;
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, int ACT, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 2) k_gemm_ffma(const GemmArgs p) {
   static_assert((BM / TM) * (BN / TN) == NTHREADS, "tile/thread mismatch");
   static_assert(TM == 4 || TM == 8, "TM");
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_gemm_ffma(const GemmArgs p) {
       int idx = tid + i * NTHREADS;
       if (BN * 4 >= NTHREADS * (i + 1) || idx < BN * 4) {
         int n = n0 + (idx >> 2), k = k0 + ((idx & 3) << 2);
-        b_reg[i] = *reinterpret_cast<const float4*>(p.W + (size_t)n * p.K + k);
+        b_reg[i] = __ldg(reinterpret_cast<const float4*>(p.W + (size_t)n * p.K + k));
       }
     }
   };
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_gemm_ffma(const GemmArgs p) {
   load_regs(0);
   store_smem(0);
   __syncthreads();
+#pragma unroll 1
   for (int t = 0; t < num_tiles; ++t) {
     const int buf = t & 1;
     if (t + 1 < num_tiles) load_regs((t + 1) * BK);
@@ -109,27 +111,48 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_gemm_ffma(const GemmArgs p) {
   }
 
   // ------------------------------------------------------------------ epilogue
+  float4 bias4[GN];
+#pragma unroll
+  for (int gn = 0; gn < GN; ++gn)
+    bias4[gn] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + gn * (BN / 2) + tx * 4))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + (i >> 2) * (BM / 2) + ty * 4 + (i & 3);
     const bool live = m < M;
     float cscale = 1.f;
-    if (live && p.scale_len) cscale = tsd_cutoff_fn(p.scale_len[m], p.cutoff, p.smooth);
+    if (EPI == TSD_EPI_SCALE && live) cscale = tsd_cutoff_fn(p.scale_len[m], p.cutoff, p.smooth);
+    const float* emb_row = (EPI == TSD_EPI_MULEMB && live) ? p.mul_emb + (size_t)(p.mul_code[m] & 0xffff) * p.N : nullptr;
     float dot = 0.f;
 #pragma unroll
     for (int gn = 0; gn < GN; ++gn) {
       const int n = n0 + gn * (BN / 2) + tx * 4;
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = live ? tsd_epilogue(p, m, n + j, acc[i][gn * 4 + j], cscale) : 0.f;
-      if (p.out_vec) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dot = fmaf(v[j], p.w3[n + j], dot);
+      float4 o;
+      o.x = tsd_act_t<ACT>(acc[i][gn * 4 + 0] + bias4[gn].x);
+      o.y = tsd_act_t<ACT>(acc[i][gn * 4 + 1] + bias4[gn].y);
+      o.z = tsd_act_t<ACT>(acc[i][gn * 4 + 2] + bias4[gn].z);
+      o.w = tsd_act_t<ACT>(acc[i][gn * 4 + 3] + bias4[gn].w);
+      if (EPI == TSD_EPI_SCALE) {
+        o.x *= cscale; o.y *= cscale; o.z *= cscale; o.w *= cscale;
+      }
+      if (EPI == TSD_EPI_MULEMB && live) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + n));
+        o.x *= e.x; o.y *= e.y; o.z *= e.z; o.w *= e.w;
+      }
+      if (EPI == TSD_EPI_PLAIN && p.residual && live) {
+        const float4 r = *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + n);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      if (EPI == TSD_EPI_DOT) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w3 + n));
+        if (live) {
+          dot = fmaf(o.x, w.x, dot); dot = fmaf(o.y, w.y, dot); dot = fmaf(o.z, w.z, dot); dot = fmaf(o.w, w.w, dot);
+        }
       } else if (live) {
-        *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = o;
       }
     }
-    if (p.out_vec) {
+    if (EPI == TSD_EPI_DOT) {
       // the TX threads that share row m are consecutive lanes (TX is 16 or 32): butterfly sum
 #pragma unroll
       for (int o = TX / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(TSD_FULL_MASK, dot, o);
@@ -141,12 +164,33 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_gemm_ffma(const GemmArgs p) {
   }
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, int ACT, int EPI>
 int launch(const GemmArgs& g, cudaStream_t stream) {
   dim3 grid(tsd_ceil_div(g.M_cap, BM), g.N / BN);
-  k_gemm_ffma<BM, BN, TM, TN><<<grid, NTHREADS, 0, stream>>>(g);
+  k_gemm_ffma<BM, BN, TM, TN, ACT, EPI><<<grid, NTHREADS, 0, stream>>>(g);
   TSD_LAUNCH_CHECK();
   return TSD_OK;
+}
+
+template <int BM, int BN, int TM, int TN, int EPI>
+int launch_act(const GemmArgs& g, cudaStream_t stream) {
+  switch (g.act) {
+    case TSD_ACT_NONE: return launch<BM, BN, TM, TN, TSD_ACT_NONE, EPI>(g, stream);
+    case TSD_ACT_RELU: return launch<BM, BN, TM, TN, TSD_ACT_RELU, EPI>(g, stream);
+    case TSD_ACT_SWISH: return launch<BM, BN, TM, TN, TSD_ACT_SWISH, EPI>(g, stream);
+    case TSD_ACT_SSP: return launch<BM, BN, TM, TN, TSD_ACT_SSP, EPI>(g, stream);
+    default: return TSD_ERR_UNSUPPORTED;
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_epi(const GemmArgs& g, int epi, cudaStream_t stream) {
+  switch (epi) {
+    case TSD_EPI_PLAIN: return launch_act<BM, BN, TM, TN, TSD_EPI_PLAIN>(g, stream);
+    case TSD_EPI_SCALE: return launch_act<BM, BN, TM, TN, TSD_EPI_SCALE>(g, stream);
+    case TSD_EPI_MULEMB: return launch_act<BM, BN, TM, TN, TSD_EPI_MULEMB>(g, stream);
+    default: return TSD_ERR_UNSUPPORTED;
+  }
 }
 
 }  // namespace
@@ -154,16 +198,20 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
 int tsd_gemm_ffma(const GemmArgs& g, cudaStream_t stream) {
   TSD_REQUIRE(g.W && g.K % BK == 0 && g.K > 0 && g.N > 0 && g.M_cap >= 0);
   TSD_REQUIRE(g.a_kind == TSD_A_EDGE_MLP0 || g.A);
+  const int epi = tsd_gemm_epi_kind(g);
+  TSD_REQUIRE(epi >= 0);
   if (g.M_cap == 0) return TSD_OK;
-  if (g.out_vec) {
-    // final-dot epilogue needs the whole output row inside one CTA
-    if (g.N == 128) return launch<128, 128, 8, 8>(g, stream);
-    if (g.N == 64) return launch<128, 64, 8, 4>(g, stream);
+  if (epi == TSD_EPI_DOT) {
+    // the row-dot epilogue needs the whole output row inside one CTA
+    if (g.N == 128) return launch_act<128, 128, 8, 8, TSD_EPI_DOT>(g, stream);
+    if (g.N == 64) return launch_act<128, 64, 8, 4, TSD_EPI_DOT>(g, stream);
     return TSD_ERR_UNSUPPORTED;
   }
   TSD_REQUIRE(g.C);
   const bool small_m = g.M_cap <= 8192;  // node-level GEMMs: favour more CTAs over tile reuse
-  if (g.N % 128 == 0) return small_m ? launch<32, 128, 4, 4>(g, stream) : launch<128, 128, 8, 8>(g, stream);
-  if (g.N % 64 == 0) return small_m ? launch<64, 64, 4, 4>(g, stream) : launch<128, 64, 8, 4>(g, stream);
+  if (g.N % 128 == 0)
+    return small_m ? launch_epi<32, 128, 4, 4>(g, epi, stream) : launch_epi<128, 128, 8, 8>(g, epi, stream);
+  if (g.N % 64 == 0)
+    return small_m ? launch_epi<64, 64, 4, 4>(g, epi, stream) : launch_epi<128, 64, 8, 4>(g, epi, stream);
   return TSD_ERR_UNSUPPORTED;
 }

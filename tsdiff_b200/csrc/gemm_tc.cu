@@ -1,20 +1,26 @@
 // Tensor-core realisation of the fused linear-layer GEMM (gemm.cuh) for sm_100a:
-// tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32 accumulation in TMEM).
+// tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32 accumulation in TMEM), operands
+// staged in shared memory by TMA.
 //
-//   CTA tile   : 128 rows x N (N = 64 / 128 / 256 = the whole output row, so the epilogue
-//                can fuse bias / activation / cutoff / row-dot), K streamed in 32-float
-//                (128-byte) panels through a 3-stage shared-memory ring
-//   operands   : A panel (128 x 32) is PRODUCED by the threads (the prologue of gemm.cuh:
-//                RBF-free edge MLP layer 0, bond-embedding gating, pair products) and
-//                written straight into the UMMA canonical K-major SWIZZLE_128B layout;
-//                W panel (N x 32) is copied from the live nn.Linear weight the same way
-//   MMA        : one elected thread issues 4 x (M128 x N x K8) tcgen05.mma per panel and
-//                tcgen05.commit's the stage's "empty" mbarrier; accumulator = N TMEM columns
-//   epilogue   : 8 warps tcgen05.ld their lane quarter (32 rows) x half of the columns,
-//                apply the epilogue in registers and store / row-reduce
-//
-// The generic-proxy shared-memory writes are made visible to the tensor core (async proxy)
-// with fence.proxy.async before the CTA barrier that precedes the MMA issue.
+//   CTA tile   : 128 rows x N (N = 64 / 128 / 256 = the whole output row, so the epilogue can
+//                fuse bias / activation / cutoff / bond-embedding gate / row-dot), K streamed
+//                in 32-float (128-byte) panels through a 4-stage shared-memory ring
+//   warp roles : warp 0  TMA producer  (one lane: cp.async.bulk.tensor of the W panel and, for
+//                         a dense A, of the A panel; SWIZZLE_128B tensor maps write the UMMA
+//                         canonical K-major layout directly; mbarrier complete_tx)
+//                warp 1  MMA issuer    (one lane: 4 x tcgen05.mma M128 x N x K8 per panel,
+//                         tcgen05.commit releases the stage)
+//                warps 4-7 A producers (only when the A operand is COMPUTED by a prologue of
+//                         gemm.cuh -- edge MLP layer 0, bond-embedding gating, pair products:
+//                         values are written with the same swizzle, fence.proxy.async, arrive)
+//                all 8 warps epilogue  (tcgen05.ld of their TMEM lane quarter x column half,
+//                         epilogue in registers, float4 stores or row-dot)
+//   pipelines  : full[s]  (TMA bytes + producer arrivals -> MMA), empty[s] (MMA commit ->
+//                producers), accum (last commit -> epilogue)
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace {
@@ -22,8 +28,12 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // floats per panel row = 128 bytes = one swizzle atom row
 constexpr int TC_THREADS = 256;
-constexpr int TC_STAGES = 2;
+// dense-A kernels: 2 stages (~97 KB at N = 256) so TWO CTAs share an SM (2 x 256 TMEM columns) and every
+// tile of a batch-100 step is resident in a single wave; computed-A kernels: 4 stages, one CTA per SM
+__host__ __device__ constexpr int tc_stages(int akind) { return akind == TSD_A_PLAIN ? 2 : 4; }
 constexpr int TC_A_PANEL_BYTES = TC_BM * TC_BK * 4;  // 16 KiB
+constexpr int TC_GROUP_THREADS = 64;                 // two warps per A-producer group
+constexpr int TC_GROUPS = 3;                         // warps 2-3, 4-5, 6-7
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -44,6 +54,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// 2-D tiled TMA load global -> shared, completion signalled on `bar` (complete_tx::bytes).
+// c0 = innermost (K) element coordinate, c1 = row coordinate.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot)                                                     \
+  do {                                                                     \
+    if (p.dbg && blockIdx.x == 0) p.dbg[slot] = gtimer();                  \
+  } while (0)
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -95,8 +133,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // byte offset of the 16-byte chunk `c` (4 floats) of row `r` inside a K-major SW128 panel
+// (identical to what a SWIZZLE_128B tensor map writes for a [rows][32 float] box)
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+  return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
 }
 
 // fast-math activations: this arithmetic mode already carries the TF32 bound, so the SFU
@@ -105,41 +144,73 @@ template <int ACT>
 __device__ __forceinline__ float tc_act(float x) {
   if (ACT == TSD_ACT_RELU) return fmaxf(x, 0.f);
   if (ACT == TSD_ACT_SWISH) return __fdividef(x, 1.f + __expf(-x));
-  if (ACT == TSD_ACT_SSP) return (x > 15.f ? x : __logf(1.f + __expf(x))) - TSD_SSP_SHIFT;
-  if (ACT == TSD_ACT_SOFTPLUS) return x > 15.f ? x : __logf(1.f + __expf(x));
+  // branch-free softplus: max(x,0) + log(1 + exp(-|x|))
+  if (ACT == TSD_ACT_SSP) return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))) - TSD_SSP_SHIFT;
+  if (ACT == TSD_ACT_SOFTPLUS) return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
   return x;
 }
 
-enum { TC_EPI_PLAIN = 0, TC_EPI_SCALE = 1, TC_EPI_MULEMB = 2, TC_EPI_DOT = 3 };
 
-// Software pipeline: two shared-memory stages + one panel of register prefetch.  Iteration kb
-//   waits until the MMAs that read stage kb%2 retired, stores the prefetched panel, issues the
-//   global loads of panel kb+1 (in flight across the CTA barrier and the MMA issue), then one
-//   thread issues the 4 MMAs of panel kb.  ~98 KB smem / CTA -> two CTAs per SM hide each
-//   other's load latency; 2 x 256 TMEM columns fill the SM's 512.
-template <int ACT, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tf32(const GemmArgs p, int tmem_cols) {
+// A-operand prologue with the fast activations of this arithmetic mode
+template <int AKIND>
+__device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k) {
+  if (AKIND == TSD_A_EDGE_MLP0) {
+    const float l = p.len[m];
+    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w0 + k));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.b0 + k));
+    const float4 x = make_float4(fmaf(l, w.x, b.x), fmaf(l, w.y, b.y), fmaf(l, w.z, b.z), fmaf(l, w.w, b.w));
+    switch (p.act0) {  // uniform
+      case TSD_ACT_SWISH:
+        return make_float4(tc_act<TSD_ACT_SWISH>(x.x), tc_act<TSD_ACT_SWISH>(x.y), tc_act<TSD_ACT_SWISH>(x.z),
+                           tc_act<TSD_ACT_SWISH>(x.w));
+      case TSD_ACT_RELU:
+        return make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+      case TSD_ACT_SSP:
+        return make_float4(tc_act<TSD_ACT_SSP>(x.x), tc_act<TSD_ACT_SSP>(x.y), tc_act<TSD_ACT_SSP>(x.z),
+                           tc_act<TSD_ACT_SSP>(x.w));
+      default:
+        return x;
+    }
+  }
+  return tsd_load_a4_t<AKIND>(p, m, k);
+}
+
+template <int ACT, int EPI, int AKIND>
+__global__ void __launch_bounds__(TC_THREADS, AKIND == TSD_A_PLAIN ? 2 : 1)
+    k_gemm_tf32(const GemmArgs p, int tmem_cols, const __grid_constant__ CUtensorMap map_a,
+                const __grid_constant__ CUtensorMap map_w) {
   extern __shared__ uint8_t smem_dyn[];
+  constexpr int TC_STAGES = tc_stages(AKIND);
+  __shared__ uint64_t bar_full[TC_STAGES];
   __shared__ uint64_t bar_empty[TC_STAGES];
   __shared__ uint64_t bar_accum;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_dot[TC_BM];
 
+  if (threadIdx.x == 0) TC_STAMP(0);
   const int M = p.M_ptr ? min(*p.M_ptr, p.M_cap) : p.M_cap;
   const int m0 = blockIdx.x * TC_BM;
   if (m0 >= M) return;  // uniform across the CTA, before any allocation
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K = p.K;
-  const uint32_t stage_bytes = TC_A_PANEL_BYTES + (uint32_t)N * TC_BK * 4;
+  if (tid == 0) TC_STAMP(1);
+  constexpr bool dense_a = AKIND == TSD_A_PLAIN;
+  const uint32_t b_panel_bytes = (uint32_t)N * TC_BK * 4;
+  const uint32_t stage_bytes = TC_A_PANEL_BYTES + b_panel_bytes;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) mbar_init(&bar_empty[s], 1);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&bar_full[s], dense_a ? 1u : 1u + TC_GROUP_THREADS);
+      mbar_init(&bar_empty[s], 1);
+    }
     mbar_init(&bar_accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    if (dense_a) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
   }
-  if (warp == 0) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"((uint32_t)tmem_cols)
                  : "memory");
@@ -149,109 +220,145 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tf32(const GemmArgs p, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = umma_idesc_tf32(N);
-
-  constexpr int A_LD = (TC_BM * 8) / TC_THREADS;  // 4 float4 per thread per panel
-  constexpr int B_LD = (256 * 8) / TC_THREADS;    // up to 8 (N = 256)
-  float4 ra[A_LD], rb[B_LD];
-  const int b_items = N * 8;
-  auto load_regs = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < A_LD; ++i) {
-      int idx = tid + i * TC_THREADS;
-      int m = m0 + (idx >> 3);
-      ra[i] = m < M ? tsd_load_a4(p, m, k0 + ((idx & 7) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int i = 0; i < B_LD; ++i) {
-      int idx = tid + i * TC_THREADS;
-      if (idx < b_items)
-        rb[i] = __ldg(reinterpret_cast<const float4*>(p.W + (size_t)(idx >> 3) * K + k0 + ((idx & 7) << 2)));
-    }
-  };
-  auto store_smem = [&](uint8_t* a_panel, uint8_t* b_panel) {
-#pragma unroll
-    for (int i = 0; i < A_LD; ++i) {
-      int idx = tid + i * TC_THREADS;
-      *reinterpret_cast<float4*>(a_panel + sw128_off(idx >> 3, idx & 7)) = ra[i];
-    }
-#pragma unroll
-    for (int i = 0; i < B_LD; ++i) {
-      int idx = tid + i * TC_THREADS;
-      if (idx < b_items) *reinterpret_cast<float4*>(b_panel + sw128_off(idx >> 3, idx & 7)) = rb[i];
-    }
-  };
-
   const int num_kb = K / TC_BK;
-  load_regs(0);
-  for (int kb = 0; kb < num_kb; ++kb) {
-    const int s = kb % TC_STAGES, round = kb / TC_STAGES;
-    if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));  // MMAs that read this stage retired
-    uint8_t* a_panel = smem_gen + (size_t)s * stage_bytes;
-    store_smem(a_panel, a_panel + TC_A_PANEL_BYTES);
-    if (kb + 1 < num_kb) load_regs((kb + 1) * TC_BK);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint64_t adesc = umma_desc_sw128(smem_base + (uint32_t)s * stage_bytes);
-      const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)s * stage_bytes + TC_A_PANEL_BYTES);
+  if (tid == 0) TC_STAMP(2);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx = b_panel_bytes + (dense_a ? TC_A_PANEL_BYTES : 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+        if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));
+        uint8_t* a_panel = smem_gen + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&bar_full[s], tx);
+        if (dense_a) tma_load_2d(a_panel, &map_a, &bar_full[s], kb * TC_BK, m0);
+        tma_load_2d(a_panel + TC_A_PANEL_BYTES, &map_w, &bar_full[s], kb * TC_BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+        mbar_wait(&bar_full[s], (uint32_t)(round & 1));
+        if (kb < 8) TC_STAMP(8 + kb);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_base + (uint32_t)s * stage_bytes);
+        const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)s * stage_bytes + TC_A_PANEL_BYTES);
 #pragma unroll
-      for (int kk = 0; kk < TC_BK / 8; ++kk)  // UMMA K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
-        umma_tf32(tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
-      umma_commit(&bar_empty[s]);
-      if (kb == num_kb - 1) umma_commit(&bar_accum);
+        for (int kk = 0; kk < TC_BK / 8; ++kk)  // UMMA K = 8 tf32 = 32 bytes: start address += 2 (x16 B)
+          umma_tf32(tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+        umma_commit(&bar_empty[s]);
+        if (kb == num_kb - 1) umma_commit(&bar_accum);
+      }
+      TC_STAMP(3);
+    }
+  } else if (warp >= 2 && !dense_a) {
+    // ------------------------------------------------------------ A producers (computed operand)
+    // three groups of two warps take panels round-robin: the global-load / SFU latency of one
+    // panel (which the proxy fence of its own threads cannot overlap) hides behind the other
+    // groups' panels, and 192 threads share the prologue arithmetic
+    const int group = (warp - 2) >> 1;
+    const int t = tid - 64 - group * TC_GROUP_THREADS;
+    constexpr int ITEMS = (TC_BM * 8) / TC_GROUP_THREADS;  // float4 per thread per panel
+    for (int kb = group; kb < num_kb; kb += TC_GROUPS) {
+      const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+      if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));
+      uint8_t* a_panel = smem_gen + (size_t)s * stage_bytes;
+      const int k0 = kb * TC_BK;
+#pragma unroll
+      for (int half_pass = 0; half_pass < 2; ++half_pass) {
+        float4 v[ITEMS / 2];
+#pragma unroll
+        for (int i = 0; i < ITEMS / 2; ++i) {
+          int idx = t + (half_pass * (ITEMS / 2) + i) * TC_GROUP_THREADS;
+          int m = m0 + (idx >> 3);
+          v[i] = m < M ? tc_load_a4<AKIND>(p, m, k0 + ((idx & 7) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS / 2; ++i) {
+          int idx = t + (half_pass * (ITEMS / 2) + i) * TC_GROUP_THREADS;
+          *reinterpret_cast<float4*>(a_panel + sw128_off(idx >> 3, idx & 7)) = v[i];
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+      mbar_arrive(&bar_full[s]);
     }
   }
+  __syncwarp();
 
   // ------------------------------------------------------------------ epilogue
+  // tcgen05.ld hands every thread ONE output row (32 consecutive columns per load).  Storing
+  // that straight to global memory makes each warp store touch 32 different 128-byte lines, so
+  // each warp transposes its 32x32 chunk through the now idle pipeline shared memory and writes
+  // 4 full 128-byte line segments per instruction.  (The activations are branch-free on
+  // purpose: a `x > t ? x : f(x)` softplus compiled to one branch per element and serialised
+  // the MUFU latency -- 2.1 us per 32-column chunk in the globaltimer timeline, now 0.4-1.0.)
   mbar_wait(&bar_accum, 0);
   tc_fence_after();
+  if (tid == 0) TC_STAMP(4);
   const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter of this warp, column half
   const int row = q * 32 + lane, m = m0 + row;
   const bool live = m < M;
   const int cols_per_half = N >> 1;
+  constexpr int TLD = 36;  // padded row stride (floats) of the transpose tile: conflict-free float4 access
+  float* tile = reinterpret_cast<float*>(smem_gen) + warp * (32 * TLD);
   float cscale = 1.f;
-  if (EPI == TC_EPI_SCALE && live) cscale = tsd_cutoff_fn(p.scale_len[m], p.cutoff, p.smooth);
+  if (EPI == TSD_EPI_SCALE && live) cscale = tsd_cutoff_fn(p.scale_len[m], p.cutoff, p.smooth);
   const float* emb_row = nullptr;
-  if (EPI == TC_EPI_MULEMB && live) emb_row = p.mul_emb + (size_t)(p.mul_code[m] & 0xffff) * N;
-  const float* res_row = (EPI == TC_EPI_PLAIN && p.residual && live) ? p.residual + (size_t)m * p.ldr : nullptr;
+  if (EPI == TSD_EPI_MULEMB) emb_row = p.mul_emb + (size_t)(live ? (p.mul_code[m] & 0xffff) : 0) * N;
   float dot = 0.f;
   for (int cc = 0; cc < cols_per_half; cc += 32) {
     const int c0 = half * cols_per_half + cc;
     uint32_t v[32];
     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-    if (live) {
-      float* dst = (EPI == TC_EPI_DOT) ? nullptr : p.C + (size_t)m * p.ldc + c0;
+    if (tid == 0 && cc == 0) TC_STAMP(16);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 o;
-        o.x = tc_act<ACT>(__uint_as_float(v[j + 0]) + b.x);
-        o.y = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
-        o.z = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
-        o.w = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
-        if (EPI == TC_EPI_SCALE) {
-          o.x *= cscale; o.y *= cscale; o.z *= cscale; o.w *= cscale;
-        }
-        if (EPI == TC_EPI_MULEMB) {
-          float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + c0 + j));
-          o.x *= e.x; o.y *= e.y; o.z *= e.z; o.w *= e.w;
-        }
-        if (EPI == TC_EPI_PLAIN && res_row) {
-          float4 r = *reinterpret_cast<const float4*>(res_row + c0 + j);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
-        if (EPI == TC_EPI_DOT) {
-          float4 w = __ldg(reinterpret_cast<const float4*>(p.w3 + c0 + j));
-          dot = fmaf(o.x, w.x, dot); dot = fmaf(o.y, w.y, dot); dot = fmaf(o.z, w.z, dot); dot = fmaf(o.w, w.w, dot);
-        } else {
-          *reinterpret_cast<float4*>(dst + j) = o;
-        }
+    for (int j = 0; j < 32; j += 4) {
+      float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 o;
+      o.x = tc_act<ACT>(__uint_as_float(v[j + 0]) + b.x);
+      o.y = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
+      o.z = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
+      o.w = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+      if (EPI == TSD_EPI_SCALE) {
+        o.x *= cscale; o.y *= cscale; o.z *= cscale; o.w *= cscale;
+      }
+      if (EPI == TSD_EPI_MULEMB) {
+        float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + c0 + j));
+        o.x *= e.x; o.y *= e.y; o.z *= e.z; o.w *= e.w;
+      }
+      if (EPI == TSD_EPI_DOT) {
+        float4 w = __ldg(reinterpret_cast<const float4*>(p.w3 + c0 + j));
+        dot = fmaf(o.x, w.x, dot); dot = fmaf(o.y, w.y, dot); dot = fmaf(o.z, w.z, dot); dot = fmaf(o.w, w.w, dot);
+      } else {
+        *reinterpret_cast<float4*>(tile + lane * TLD + j) = o;
       }
     }
+    if (tid == 0 && cc == 0) TC_STAMP(17);
+    if (EPI != TSD_EPI_DOT) {
+      __syncwarp();
+      const int cg = (lane & 7) << 2;  // 8 lanes cover the 32 columns of one row: a full 128-byte line
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        const int mr = m0 + q * 32 + r;
+        float4 o = *reinterpret_cast<const float4*>(tile + r * TLD + cg);
+        if (mr < M) {
+          if (EPI == TSD_EPI_PLAIN && p.residual) {
+            const float4 rs = *reinterpret_cast<const float4*>(p.residual + (size_t)mr * p.ldr + c0 + cg);
+            o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+          }
+          *reinterpret_cast<float4*>(p.C + (size_t)mr * p.ldc + c0 + cg) = o;
+        }
+      }
+      __syncwarp();
+    }
+    if (tid == 0 && cc < 128) TC_STAMP(18 + (cc >> 5));
   }
-  if (EPI == TC_EPI_DOT) {
+  if (EPI == TSD_EPI_DOT) {
     if (half == 1) s_dot[row] = dot;
     __syncthreads();
     if (half == 0 && live) {
@@ -259,33 +366,98 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gemm_tf32(const GemmArgs p, i
       p.out_vec[m] = p.accumulate ? p.out_vec[m] + r : r;
     }
   }
+  if (tid == 0) TC_STAMP(5);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (tid == 0) TC_STAMP(6);
+  if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols)
                  : "memory");
   }
 }
 
-template <int ACT, int EPI>
-int tc_launch(const GemmArgs& g, int tmem_cols, size_t smem, cudaStream_t stream) {
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// resolved through the runtime so the library carries no link-time dependency on libcuda
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult status;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &status) == cudaSuccess &&
+        status == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// row-major fp32 matrix (rows x cols), box = box_rows x 32 floats, SWIZZLE_128B
+bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+unsigned long long* tc_dbg_buffer() {
+  static unsigned long long* buf = nullptr;
+  static bool checked = false;
+  if (!checked) {
+    checked = true;
+    const char* e = getenv("TSD_GEMM_DBG");
+    if (e && e[0] == '1') cudaMalloc(&buf, 64 * sizeof(unsigned long long));
+  }
+  return buf;
+}
+
+template <int ACT, int EPI, int AKIND>
+int tc_launch(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
+              cudaStream_t stream) {
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI, AKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  k_gemm_tf32<ACT, EPI><<<tsd_ceil_div(g.M_cap, TC_BM), TC_THREADS, smem, stream>>>(g, tmem_cols);
+  GemmArgs g = g0;
+  g.dbg = tc_dbg_buffer();
+  if (g.dbg) {
+    cudaMemsetAsync(g.dbg, 0, 64 * sizeof(unsigned long long), stream);
+  }
+  k_gemm_tf32<ACT, EPI, AKIND><<<tsd_ceil_div(g.M_cap, TC_BM), TC_THREADS, smem, stream>>>(g, tmem_cols, map_a, map_w);
   TSD_LAUNCH_CHECK();
+  if (g.dbg) {
+    unsigned long long hb[64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hb, g.dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+    unsigned long long* dbgv = hb;
+    unsigned long long t0 = dbgv[0];
+    fprintf(stderr, "[tc dbg] act=%d epi=%d akind=%d M_cap=%d N=%d K=%d | setup %llu alloc %llu | mma_done %llu accum %llu epi %llu end %llu | full:",
+            ACT, EPI, AKIND, g.M_cap, g.N, g.K, dbgv[1] - t0, dbgv[2] - t0, dbgv[3] - t0, dbgv[4] - t0, dbgv[5] - t0,
+            dbgv[6] - t0);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %llu", dbgv[8 + i] ? dbgv[8 + i] - t0 : 0ull);
+    fprintf(stderr, " | epi-detail:");
+    for (int i = 16; i < 22; ++i) fprintf(stderr, " %llu", dbgv[i] ? dbgv[i] - t0 : 0ull);
+    fprintf(stderr, "\n");
+  }
   return TSD_OK;
 }
 
-template <int EPI>
-int tc_dispatch_act(const GemmArgs& g, int tmem_cols, size_t smem, cudaStream_t stream) {
+template <int EPI, int AKIND>
+int tc_dispatch_act(const GemmArgs& g, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
+                    cudaStream_t stream) {
   switch (g.act) {
-    case TSD_ACT_NONE: return tc_launch<TSD_ACT_NONE, EPI>(g, tmem_cols, smem, stream);
-    case TSD_ACT_RELU: return tc_launch<TSD_ACT_RELU, EPI>(g, tmem_cols, smem, stream);
-    case TSD_ACT_SWISH: return tc_launch<TSD_ACT_SWISH, EPI>(g, tmem_cols, smem, stream);
-    case TSD_ACT_SSP: return tc_launch<TSD_ACT_SSP, EPI>(g, tmem_cols, smem, stream);
+    case TSD_ACT_NONE: return tc_launch<TSD_ACT_NONE, EPI, AKIND>(g, tmem_cols, smem, map_a, map_w, stream);
+    case TSD_ACT_RELU: return tc_launch<TSD_ACT_RELU, EPI, AKIND>(g, tmem_cols, smem, map_a, map_w, stream);
+    case TSD_ACT_SWISH: return tc_launch<TSD_ACT_SWISH, EPI, AKIND>(g, tmem_cols, smem, map_a, map_w, stream);
+    case TSD_ACT_SSP: return tc_launch<TSD_ACT_SSP, EPI, AKIND>(g, tmem_cols, smem, map_a, map_w, stream);
     default: return TSD_ERR_UNSUPPORTED;
   }
 }
@@ -297,12 +469,40 @@ int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream) {
   if (!(g.N == 64 || g.N == 128 || g.N == 256) || g.K % TC_BK != 0 || g.K <= 0) return TSD_ERR_UNSUPPORTED;
   if (g.M_cap < 1024) return TSD_ERR_UNSUPPORTED;
   TSD_REQUIRE(g.W && (g.a_kind == TSD_A_EDGE_MLP0 || g.A) && (g.out_vec || g.C));
+  const int epi = tsd_gemm_epi_kind(g);
+  if (epi < 0) return TSD_ERR_UNSUPPORTED;
+  if (g.a_kind == TSD_A_PLAIN && g.lda != g.K) return TSD_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g.W) & 15) || (g.a_kind == TSD_A_PLAIN && (reinterpret_cast<uintptr_t>(g.A) & 15)))
+    return TSD_ERR_UNSUPPORTED;  // TMA needs 16-byte aligned global addresses
+  CUtensorMap map_a, map_w;
+  if (!make_tensor_map(&map_w, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint32_t)g.N)) return TSD_ERR_UNSUPPORTED;
+  if (g.a_kind == TSD_A_PLAIN) {
+    if (!make_tensor_map(&map_a, g.A, (uint64_t)g.M_cap, (uint64_t)g.K, TC_BM)) return TSD_ERR_UNSUPPORTED;
+  } else {
+    map_a = map_w;  // unused by the kernel
+  }
   const int tmem_cols = g.N < 32 ? 32 : g.N;  // power of two >= 32
-  const size_t smem = (size_t)TC_STAGES * (TC_A_PANEL_BYTES + (size_t)g.N * TC_BK * 4) + 1024;
-  const int n_epi = (g.scale_len != nullptr) + (g.mul_emb != nullptr) + (g.out_vec != nullptr);
-  if (n_epi > 1 || (n_epi == 1 && g.residual)) return TSD_ERR_UNSUPPORTED;
-  if (g.out_vec) return tc_dispatch_act<TC_EPI_DOT>(g, tmem_cols, smem, stream);
-  if (g.scale_len) return tc_dispatch_act<TC_EPI_SCALE>(g, tmem_cols, smem, stream);
-  if (g.mul_emb) return tc_dispatch_act<TC_EPI_MULEMB>(g, tmem_cols, smem, stream);
-  return tc_dispatch_act<TC_EPI_PLAIN>(g, tmem_cols, smem, stream);
+  size_t smem = (size_t)tc_stages(g.a_kind) * (TC_A_PANEL_BYTES + (size_t)g.N * TC_BK * 4) + 1024;
+  if (smem < 40 * 1024) smem = 40 * 1024;  // room for the epilogue's transpose tiles (8 x 4.5 KiB)
+#define TC_GO(EPI, AKIND) return tc_dispatch_act<EPI, AKIND>(g, tmem_cols, smem, map_a, map_w, stream)
+  switch (g.a_kind) {
+    case TSD_A_PLAIN:
+      if (epi == TSD_EPI_DOT) TC_GO(TSD_EPI_DOT, TSD_A_PLAIN);
+      if (epi == TSD_EPI_SCALE) TC_GO(TSD_EPI_SCALE, TSD_A_PLAIN);
+      if (epi == TSD_EPI_PLAIN) TC_GO(TSD_EPI_PLAIN, TSD_A_PLAIN);
+      return TSD_ERR_UNSUPPORTED;
+    case TSD_A_EDGE_MLP0:  // d_emb (cat path) or d_emb * bond_emb (no-cat path)
+      if (epi == TSD_EPI_PLAIN) TC_GO(TSD_EPI_PLAIN, TSD_A_EDGE_MLP0);
+      if (epi == TSD_EPI_MULEMB) TC_GO(TSD_EPI_MULEMB, TSD_A_EDGE_MLP0);
+      return TSD_ERR_UNSUPPORTED;
+    case TSD_A_CAT:
+      if (epi == TSD_EPI_PLAIN) TC_GO(TSD_EPI_PLAIN, TSD_A_CAT);
+      return TSD_ERR_UNSUPPORTED;
+    case TSD_A_PAIR:
+      if (epi == TSD_EPI_PLAIN) TC_GO(TSD_EPI_PLAIN, TSD_A_PAIR);
+      return TSD_ERR_UNSUPPORTED;
+    default:
+      return TSD_ERR_UNSUPPORTED;
+  }
+#undef TC_GO
 }
