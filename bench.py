@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--ld-steps", type=int, default=5000, help="Langevin steps per trajectory (sampling.py default)")
     ap.add_argument("--batch", type=int, default=100, help="reactions per GPU")
     ap.add_argument("--network", default="condensenc", choices=["condensenc", "dualenc"])
-    ap.add_argument("--math", default=os.environ.get("TSDIFF_B200_MATH", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=os.environ.get("TSDIFF_B200_MATH", "tf32"), choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 tensor cores, fp32 accumulate (DESIGN.md section 4 bounds); fp32: FFMA strict parity")
     ap.add_argument("--ref-ld-steps", type=int, default=8, help="sampler steps per bounded CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -173,6 +173,10 @@ int tsd_linear(int32_t rows, const int32_t* rows_dev, const float* x, const tsd_
 int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t channels,
                          const float* x1, const float* filt, float* agg, tsd_stream_t stream);
 
+/* fp32 -> TF32 round-to-nearest (result kept in an fp32 container).  The tensor-core path reads
+ * fp32 operands by truncation; the host keeps RNE-rounded shadow copies of the weights. */
+int tsd_round_tf32(const float* src, float* dst, int64_t n, tsd_stream_t stream);
+
 /* ---- K5: one GINEConv + GINEncoder glue (replaces models/encoder/gin.py:42-73,:136-143):
  *   out_i = sum_{j->i, edge local} relu(h_j + e_ji) + (1 + eps) h_i;  hid = nn1(relu(nn0(out)))
  *   h_out = (relu_after ? relu(hid) : hid) + h_in

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "tsd_version": [],
     "tsd_launch_count": [],
     "tsd_linear": [C.c_int32, _P, _P, C.POINTER(Linear), C.c_int32, _P, C.c_int32, _P],
+    "tsd_round_tf32": [_P, _P, C.c_int64, _P],
     "tsd_cfconv_aggregate": [C.POINTER(Batch), C.POINTER(Edges), C.c_int32, _P, _P, _P, _P],
     "tsd_last_cuda_error": [],
     "tsd_error_string": [C.c_int],

@@ -99,6 +99,7 @@ extern "C" int tsd_edge_embed(const tsd_batch_t* batch, const tsd_edges_t* edges
       g.mul_emb = enc->bond_emb;
       g.mul_code = code;
       g.C = out;
+      g.round_out = 1;
     }
     TSD_TRY(tsd_gemm(g, math, s));
   }
@@ -114,10 +115,12 @@ extern "C" int tsd_edge_embed(const tsd_batch_t* batch, const tsd_edges_t* edges
     g.code = code;
     g.act = enc->cat_act;
     g.C = tmp;
+    g.round_out = 1;  // feeds cat2
     TSD_TRY(tsd_gemm(g, math, s));
     GemmArgs g2 = edge_gemm(batch, edges, *enc->cat2);
     g2.A = tmp;
     g2.C = out;
+    g2.round_out = 1;  // edge_attr feeds the filter networks and the pair MLP
     TSD_TRY(tsd_gemm(g2, math, s));
   }
   return TSD_OK;
@@ -135,6 +138,7 @@ extern "C" int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edg
   g.A = edge_attr;
   g.act = TSD_ACT_SSP;
   g.C = ef0;
+  g.round_out = 1;  // feeds nn2
   TSD_TRY(tsd_gemm(g, math, s));
   g = edge_gemm(batch, edges, blk->nn2);
   g.A = ef0;
@@ -204,6 +208,7 @@ extern "C" int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, 
   g.col = edges->col;
   g.act = mlp->act;
   g.C = ef0;
+  g.round_out = 1;  // feeds l1
   TSD_TRY(tsd_gemm(g, math, s));
   g = edge_gemm(batch, edges, mlp->l1);
   g.A = ef0;

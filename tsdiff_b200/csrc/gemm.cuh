@@ -51,6 +51,7 @@ struct GemmArgs {
   const float* b3;
   float* out_vec;
   int accumulate;
+  int round_out;           // tf32 mode: round stored outputs to TF32 (RNE) because a tensor-core GEMM consumes them
   unsigned long long* dbg;  // optional timeline buffer (TSD_GEMM_DBG=1), CTA 0 writes globaltimer stamps
 };
 

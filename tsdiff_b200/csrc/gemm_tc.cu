@@ -151,6 +151,19 @@ __device__ __forceinline__ float tc_act(float x) {
 }
 
 
+// The MMA reads fp32 operands as TF32 by TRUNCATION (it ignores the low 13 mantissa bits), which
+// biases every product.  Operands are therefore pre-rounded to nearest: weights once per engine
+// (tsd_round_tf32), computed A operands here, and GEMM outputs that feed another GEMM in the
+// producing epilogue (GemmArgs.round_out).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) {
+  return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+}
+
 // A-operand prologue with the fast activations of this arithmetic mode
 template <int AKIND>
 __device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k) {
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, AKIND == TSD_A_PLAIN ? 2 : 1)
         for (int i = 0; i < ITEMS / 2; ++i) {
           int idx = t + (half_pass * (ITEMS / 2) + i) * TC_GROUP_THREADS;
           int m = m0 + (idx >> 3);
-          v[i] = m < M ? tc_load_a4<AKIND>(p, m, k0 + ((idx & 7) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[i] = m < M ? tf32_rn4(tc_load_a4<AKIND>(p, m, k0 + ((idx & 7) << 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < ITEMS / 2; ++i) {
@@ -330,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, AKIND == TSD_A_PLAIN ? 2 : 1)
         float4 e = __ldg(reinterpret_cast<const float4*>(emb_row + c0 + j));
         o.x *= e.x; o.y *= e.y; o.z *= e.z; o.w *= e.w;
       }
+      if (EPI != TSD_EPI_DOT && p.round_out) o = tf32_rn4(o);
       if (EPI == TSD_EPI_DOT) {
         float4 w = __ldg(reinterpret_cast<const float4*>(p.w3 + c0 + j));
         dot = fmaf(o.x, w.x, dot); dot = fmaf(o.y, w.y, dot); dot = fmaf(o.z, w.z, dot); dot = fmaf(o.w, w.w, dot);
@@ -505,4 +519,22 @@ int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream) {
       return TSD_ERR_UNSUPPORTED;
   }
 #undef TC_GO
+}
+
+// elementwise round-to-nearest fp32 -> TF32 (kept in an fp32 container): weight shadow copies
+__global__ void k_round_tf32(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
+    dst[i] = __uint_as_float(r);
+  }
+}
+
+extern "C" int tsd_round_tf32(const float* src, float* dst, int64_t n, tsd_stream_t stream) {
+  TSD_REQUIRE(src && dst && n >= 0);
+  if (n == 0) return TSD_OK;
+  k_round_tf32<<<(unsigned)((n + 255) / 256), 256, 0, tsd_cu(stream)>>>(src, dst, (long long)n);
+  TSD_LAUNCH_CHECK();
+  return TSD_OK;
 }

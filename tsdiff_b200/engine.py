@@ -118,17 +118,35 @@ class _Scratch:
                      for _ in range(n_node_bufs)]
 
 
-def _edge_encoder_struct(enc, act, cat=None, cat_act="none"):
+class _WeightView:
+    """Maps an nn.Linear weight to the tensor the GEMM reads.  fp32 mode: the live parameter
+    itself.  tf32 mode: a round-to-nearest TF32 shadow copy (the tensor cores read fp32 operands
+    by truncation; weights are constant while sampling, so they are rounded once per engine)."""
+
+    def __init__(self, math):
+        self.tf32 = math == "tf32"
+        self.keep = []
+
+    def __call__(self, w):
+        if not self.tf32:
+            return w
+        shadow = torch.empty_like(w)
+        L.check(L.load().tsd_round_tf32(L.ptr(w), L.ptr(shadow), w.numel(), _stream()), "tsd_round_tf32")
+        self.keep.append(shadow)
+        return shadow
+
+
+def _edge_encoder_struct(enc, act, cat=None, cat_act="none", wv=lambda w: w):
     """enc: layers.MLPEdgeEncoder; cat: nn.Sequential(Linear, act, Linear) or None."""
     keep = []
     s = L.EdgeEncoder()
     s.lin0 = L.linear(enc.mlp.layers[0].weight, enc.mlp.layers[0].bias)
-    s.lin1 = L.linear(enc.mlp.layers[1].weight, enc.mlp.layers[1].bias)
+    s.lin1 = L.linear(wv(enc.mlp.layers[1].weight), enc.mlp.layers[1].bias)
     s.bond_emb = enc.bond_emb.weight.data_ptr()
     s.act = L.ACT[act]
     if cat is not None:
-        c0 = L.linear(cat[0].weight, cat[0].bias)
-        c2 = L.linear(cat[2].weight, cat[2].bias)
+        c0 = L.linear(wv(cat[0].weight), cat[0].bias)
+        c2 = L.linear(wv(cat[2].weight), cat[2].bias)
         keep += [c0, c2]
         s.cat0 = C.pointer(c0)
         s.cat2 = C.pointer(c2)
@@ -136,31 +154,31 @@ def _edge_encoder_struct(enc, act, cat=None, cat_act="none"):
     return s, keep
 
 
-def _interaction_struct(blk):
+def _interaction_struct(blk, wv=lambda w: w):
     s = L.Interaction()
-    s.nn0 = L.linear(blk.conv.nn[0].weight, blk.conv.nn[0].bias)
-    s.nn2 = L.linear(blk.conv.nn[2].weight, blk.conv.nn[2].bias)
-    s.lin1 = L.linear(blk.conv.lin1.weight, None)
-    s.lin2 = L.linear(blk.conv.lin2.weight, blk.conv.lin2.bias)
-    s.lin = L.linear(blk.lin.weight, blk.lin.bias)
+    s.nn0 = L.linear(wv(blk.conv.nn[0].weight), blk.conv.nn[0].bias)
+    s.nn2 = L.linear(wv(blk.conv.nn[2].weight), blk.conv.nn[2].bias)
+    s.lin1 = L.linear(wv(blk.conv.lin1.weight), None)
+    s.lin2 = L.linear(wv(blk.conv.lin2.weight), blk.conv.lin2.bias)
+    s.lin = L.linear(wv(blk.lin.weight), blk.lin.bias)
     s.cutoff = float(blk.conv.cutoff)
     s.smooth = int(bool(blk.conv.smooth))
     return s
 
 
-def _pair_mlp_struct(mlp):
+def _pair_mlp_struct(mlp, wv=lambda w: w):
     s = L.PairMlp()
-    s.l0 = L.linear(mlp.layers[0].weight, mlp.layers[0].bias)
-    s.l1 = L.linear(mlp.layers[1].weight, mlp.layers[1].bias)
+    s.l0 = L.linear(wv(mlp.layers[0].weight), mlp.layers[0].bias)
+    s.l1 = L.linear(wv(mlp.layers[1].weight), mlp.layers[1].bias)
     s.l2 = L.linear(mlp.layers[2].weight, mlp.layers[2].bias)
     s.act = L.ACT[mlp.act]
     return s
 
 
-def _gine_struct(conv, relu_after):
+def _gine_struct(conv, relu_after, wv=lambda w: w):
     s = L.Gine()
-    s.nn0 = L.linear(conv.nn.layers[0].weight, conv.nn.layers[0].bias)
-    s.nn1 = L.linear(conv.nn.layers[1].weight, conv.nn.layers[1].bias)
+    s.nn0 = L.linear(wv(conv.nn.layers[0].weight), conv.nn.layers[0].bias)
+    s.nn1 = L.linear(wv(conv.nn.layers[1].weight), conv.nn.layers[1].bias)
     s.eps = conv.eps.data_ptr()
     s.relu_after = int(relu_after)
     return s
@@ -195,6 +213,7 @@ class CondensedScoreEngine:
         r_feat = r_feat.to(torch.long).contiguous()
         p_feat = p_feat.to(torch.long).contiguous()
         self.members = []
+        self.wv = _WeightView(math)
         for m in self.models:
             z = torch.empty(max(plan.num_nodes, 1), h, dtype=torch.float32, device=plan.device)
             L.check(lib.tsd_condensed_node_embed(plan.num_nodes, L.ptr(atom_type), L.ptr(r_feat), L.ptr(p_feat),
@@ -202,9 +221,9 @@ class CondensedScoreEngine:
                                                  L.ptr(m.atom_embedding.weight), L.ptr(m.atom_feat_embedding.weight),
                                                  h // 2, L.ptr(z), _stream()), "tsd_condensed_node_embed")
             enc, keep = _edge_encoder_struct(m.edge_encoder, m.edge_encoder.mlp.act, m.edge_cat,
-                                             L_act(cfg.edge_cat_act))
-            blocks = [_interaction_struct(b) for b in m.encoder.interactions]
-            pair = _pair_mlp_struct(m.grad_dist_mlp)
+                                             L_act(cfg.edge_cat_act), self.wv)
+            blocks = [_interaction_struct(b, self.wv) for b in m.encoder.interactions]
+            pair = _pair_mlp_struct(m.grad_dist_mlp, self.wv)
             self.members.append({"z": z, "enc": enc, "keep": keep, "blocks": blocks, "pair": pair})
 
     def evaluate(self, pos):
@@ -274,15 +293,16 @@ class DualScoreEngine:
         self.atom_type = atom_type.to(torch.long).contiguous()
         act = model.edge_encoder_global.mlp.act
         cat_act = L_act(cfg.edge_cat_act) if self.ts else "none"
+        self.wv = _WeightView(math)
         self.enc_g, self._k1 = _edge_encoder_struct(model.edge_encoder_global, act,
-                                                    model.edge_cat_global if self.ts else None, cat_act)
+                                                    model.edge_cat_global if self.ts else None, cat_act, self.wv)
         self.enc_l, self._k2 = _edge_encoder_struct(model.edge_encoder_local, act,
-                                                    model.edge_cat_local if self.ts else None, cat_act)
-        self.blocks = [_interaction_struct(b) for b in model.encoder_global.interactions]
+                                                    model.edge_cat_local if self.ts else None, cat_act, self.wv)
+        self.blocks = [_interaction_struct(b, self.wv) for b in model.encoder_global.interactions]
         n_local = len(model.encoder_local.convs)
-        self.gines = [_gine_struct(c, i < n_local - 1) for i, c in enumerate(model.encoder_local.convs)]
-        self.pair_g = _pair_mlp_struct(model.grad_global_dist_mlp)
-        self.pair_l = _pair_mlp_struct(model.grad_local_dist_mlp)
+        self.gines = [_gine_struct(c, i < n_local - 1, self.wv) for i, c in enumerate(model.encoder_local.convs)]
+        self.pair_g = _pair_mlp_struct(model.grad_global_dist_mlp, self.wv)
+        self.pair_l = _pair_mlp_struct(model.grad_local_dist_mlp, self.wv)
         n = max(plan.num_nodes, 1)
         self.h0_global = torch.empty(n, h, dtype=torch.float32, device=plan.device)
         self.h0_local = torch.empty(n, h, dtype=torch.float32, device=plan.device)
