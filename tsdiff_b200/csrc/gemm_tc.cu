@@ -164,11 +164,26 @@ __device__ __forceinline__ float4 tf32_rn4(float4 v) {
   return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
 }
 
-// A-operand prologue with the fast activations of this arithmetic mode
+// A-operand prologue with the fast activations of this arithmetic mode.  A producer thread
+// always serves the same 16 rows (and the same 16-byte column chunk), so the per-row metadata
+// (length / packed bond codes / row+col atom ids) is loaded ONCE before the K loop: the panel
+// loads then have no dependent index load in front of them.
 template <int AKIND>
-__device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k) {
+__device__ __forceinline__ void tc_row_meta(const GemmArgs& p, int m, int& meta0, int& meta1) {
+  meta0 = 0;
+  meta1 = 0;
+  if (AKIND == TSD_A_EDGE_MLP0) meta0 = __float_as_int(p.len[m]);
+  if (AKIND == TSD_A_CAT) meta0 = p.code[m];
+  if (AKIND == TSD_A_PAIR) {
+    meta0 = p.row[m];
+    meta1 = p.col[m];
+  }
+}
+
+template <int AKIND>
+__device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, int meta0, int meta1) {
   if (AKIND == TSD_A_EDGE_MLP0) {
-    const float l = p.len[m];
+    const float l = __int_as_float(meta0);
     const float4 w = __ldg(reinterpret_cast<const float4*>(p.w0 + k));
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.b0 + k));
     const float4 x = make_float4(fmaf(l, w.x, b.x), fmaf(l, w.y, b.y), fmaf(l, w.z, b.z), fmaf(l, w.w, b.w));
@@ -185,7 +200,23 @@ __device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k) {
         return x;
     }
   }
-  return tsd_load_a4_t<AKIND>(p, m, k);
+  if (AKIND == TSD_A_CAT) {
+    const int hi = k >= p.H;
+    const int kk = k - (hi ? p.H : 0);
+    const int r = hi ? ((unsigned)meta0 >> 16) : (meta0 & 0xffff);
+    const float4 d = *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + kk);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)r * p.H + kk));
+    return make_float4(d.x * e.x, d.y * e.y, d.z * e.z, d.w * e.w);
+  }
+  if (AKIND == TSD_A_PAIR) {
+    if (k < p.H) {
+      const float4 a = *reinterpret_cast<const float4*>(p.h + (size_t)meta0 * p.H + k);
+      const float4 b = *reinterpret_cast<const float4*>(p.h + (size_t)meta1 * p.H + k);
+      return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+    }
+    return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + (k - p.H));
+  }
+  return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);
 }
 
 template <int ACT, int EPI, int AKIND>
@@ -275,27 +306,24 @@ __global__ void __launch_bounds__(TC_THREADS, AKIND == TSD_A_PLAIN ? 2 : 1)
     // groups' panels, and 192 threads share the prologue arithmetic
     const int group = (warp - 2) >> 1;
     const int t = tid - 64 - group * TC_GROUP_THREADS;
-    constexpr int ITEMS = (TC_BM * 8) / TC_GROUP_THREADS;  // float4 per thread per panel
+    constexpr int ITEMS = (TC_BM * 8) / TC_GROUP_THREADS;  // 16 float4 per thread per panel
+    const int chunk = t & 7, row0 = t >> 3;                // item i -> row row0 + 8 i, 16-byte chunk `chunk`
+    int meta0[ITEMS], meta1[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i)  // rows past M are clamped: they only feed output rows that are never stored
+      tc_row_meta<AKIND>(p, min(m0 + row0 + 8 * i, M - 1), meta0[i], meta1[i]);
     for (int kb = group; kb < num_kb; kb += TC_GROUPS) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));
       uint8_t* a_panel = smem_gen + (size_t)s * stage_bytes;
-      const int k0 = kb * TC_BK;
+      const int k = kb * TC_BK + (chunk << 2);
+      float4 v[ITEMS];
 #pragma unroll
-      for (int half_pass = 0; half_pass < 2; ++half_pass) {
-        float4 v[ITEMS / 2];
+      for (int i = 0; i < ITEMS; ++i)  // branch-free on purpose: a per-item `m < M` branch serialises the 16 loads
+        v[i] = tf32_rn4(tc_load_a4<AKIND>(p, min(m0 + row0 + 8 * i, M - 1), k, meta0[i], meta1[i]));
 #pragma unroll
-        for (int i = 0; i < ITEMS / 2; ++i) {
-          int idx = t + (half_pass * (ITEMS / 2) + i) * TC_GROUP_THREADS;
-          int m = m0 + (idx >> 3);
-          v[i] = m < M ? tf32_rn4(tc_load_a4<AKIND>(p, m, k0 + ((idx & 7) << 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < ITEMS / 2; ++i) {
-          int idx = t + (half_pass * (ITEMS / 2) + i) * TC_GROUP_THREADS;
-          *reinterpret_cast<float4*>(a_panel + sw128_off(idx >> 3, idx & 7)) = v[i];
-        }
-      }
+      for (int i = 0; i < ITEMS; ++i)
+        *reinterpret_cast<float4*>(a_panel + sw128_off(row0 + 8 * i, chunk)) = v[i];
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
       mbar_arrive(&bar_full[s]);
     }
