@@ -245,3 +245,85 @@ extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t*
   return tsd_launch_cfconv_aggregate(batch->num_nodes, channels, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt,
                                      agg, tsd_cu(stream));
 }
+
+static ChainStage chain_stage(const tsd_linear_t& lin, int act) {
+  ChainStage st;
+  memset(&st, 0, sizeof(st));
+  st.W = lin.weight;
+  st.bias = lin.bias;
+  st.act = act;
+  return st;
+}
+
+// Whole SchNet encoder (schnet.py:203-225).  fp32 mode: one tsd_cfconv_layer per block.  tf32
+// mode: per block ONE chained filter-network kernel on the edges, the segmented aggregation, and
+// ONE chained node kernel that also produces the next block's x1 = lin1(h') -- 3 launches per
+// block instead of 6 and no (E,H) / (N,H) intermediate round trips.
+extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                                  const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
+                                  float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, int32_t math,
+                                  tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && edge_attr && blocks && num_blocks >= 1 && h_in && h_out && ef0 && ef1 && nf0 && nf1 && nf2);
+  cudaStream_t s = tsd_cu(stream);
+  const int H = blocks[0].lin.out_features;
+  bool chain_ok = math == TSD_MATH_TF32 && (H == 128 || H == 256) && batch->num_nodes >= 1024 &&
+                  batch->edge_capacity >= 1024;
+  for (int l = 0; l < num_blocks && chain_ok; ++l) {
+    const tsd_interaction_t& b = blocks[l];
+    chain_ok = b.nn0.in_features == H && b.nn0.out_features == H && b.nn2.in_features == H && b.nn2.out_features == H &&
+               b.lin1.in_features == H && b.lin1.out_features == H && b.lin2.in_features == H &&
+               b.lin2.out_features == H && b.lin.in_features == H && b.lin.out_features == H;
+  }
+  if (!chain_ok) {
+    const float* h = h_in;
+    for (int l = 0; l < num_blocks; ++l) {
+      TSD_TRY(tsd_cfconv_layer(batch, edges, edge_attr, &blocks[l], h, h_out, ef0, ef1, nf0, nf1, nf2, math, stream));
+      h = h_out;
+    }
+    return TSD_OK;
+  }
+  // x1 of block 0
+  GemmArgs g = node_gemm(batch, blocks[0].lin1);
+  g.A = h_in;
+  g.C = nf0;
+  TSD_TRY(tsd_gemm(g, math, s));
+  const float* h = h_in;
+  for (int l = 0; l < num_blocks; ++l) {
+    const tsd_interaction_t& b = blocks[l];
+    // filter network on the edges: ef1 = nn2(ssp(nn0(edge_attr))) * C(len)
+    ChainArgs c;
+    memset(&c, 0, sizeof(c));
+    c.M_cap = batch->edge_capacity;
+    c.M_ptr = edges->num_edges;
+    c.H = H;
+    c.A = edge_attr;
+    c.num_stages = 2;
+    c.st[0] = chain_stage(b.nn0, TSD_ACT_SSP);
+    c.st[1] = chain_stage(b.nn2, TSD_ACT_NONE);
+    c.st[1].scale_len = edges->length;
+    c.st[1].cutoff = b.cutoff;
+    c.st[1].smooth = b.smooth;
+    c.st[1].store = ef1;
+    TSD_TRY(tsd_chain_tf32(c, s));
+    TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, nf0, ef1, nf1, s));
+    // node update: h' = h + lin(ssp(lin2(agg))) and, unless this is the last block, x1' = lin1_next(h')
+    memset(&c, 0, sizeof(c));
+    c.M_cap = batch->num_nodes;
+    c.H = H;
+    c.A = nf1;
+    c.st[0] = chain_stage(b.lin2, TSD_ACT_SSP);
+    c.st[1] = chain_stage(b.lin, TSD_ACT_NONE);
+    c.st[1].residual = h;
+    c.st[1].store = h_out;
+    if (l + 1 < num_blocks) {
+      c.num_stages = 3;
+      c.st[2] = chain_stage(blocks[l + 1].lin1, TSD_ACT_NONE);
+      c.st[2].store = nf0;
+    } else {
+      c.num_stages = 2;
+    }
+    TSD_TRY(tsd_chain_tf32(c, s));
+    h = h_out;
+  }
+  return TSD_OK;
+}

@@ -120,6 +120,29 @@ __device__ __forceinline__ float4 tsd_load_a4(const GemmArgs& p, int m, int k) {
   }
 }
 
+// chained H x H linear layers on one 128-row tile (gemm_chain.cu)
+struct ChainStage {
+  const float* W;         // (H, H) row-major (TF32-rounded shadow of the nn.Linear weight)
+  const float* bias;      // (H) or NULL
+  int act;
+  const float* scale_len; // (M) or NULL: multiply by the cutoff envelope C(len[m])
+  float cutoff;
+  int smooth;
+  const float* residual;  // (M, H) or NULL: added after the activation
+  float* store;           // (M, H) or NULL: result written to global memory
+};
+
+struct ChainArgs {
+  int M_cap;
+  const int* M_ptr;
+  int H;
+  const float* A;         // (M_cap, H) dense input of stage 0
+  int num_stages;         // 2 or 3
+  ChainStage st[3];
+  unsigned long long* dbg;  // optional CTA-0 timeline (TSD_GEMM_DBG=1)
+};
+
+int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream);           // gemm_chain.cu
 int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream);        // dispatch (api.cu)
 int tsd_gemm_ffma(const GemmArgs& g, cudaStream_t stream);             // gemm_ffma.cu
 int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream);             // gemm_tc.cu

@@ -166,6 +166,11 @@ def _interaction_struct(blk, wv=lambda w: w):
     return s
 
 
+def _interaction_array(blocks):
+    """Contiguous C array of tsd_interaction_t for tsd_schnet_encoder."""
+    return (L.Interaction * len(blocks))(*blocks)
+
+
 def _pair_mlp_struct(mlp, wv=lambda w: w):
     s = L.PairMlp()
     s.l0 = L.linear(wv(mlp.layers[0].weight), mlp.layers[0].bias)
@@ -222,7 +227,7 @@ class CondensedScoreEngine:
                                                  h // 2, L.ptr(z), _stream()), "tsd_condensed_node_embed")
             enc, keep = _edge_encoder_struct(m.edge_encoder, m.edge_encoder.mlp.act, m.edge_cat,
                                              L_act(cfg.edge_cat_act), self.wv)
-            blocks = [_interaction_struct(b, self.wv) for b in m.encoder.interactions]
+            blocks = _interaction_array([_interaction_struct(b, self.wv) for b in m.encoder.interactions])
             pair = _pair_mlp_struct(m.grad_dist_mlp, self.wv)
             self.members.append({"z": z, "enc": enc, "keep": keep, "blocks": blocks, "pair": pair})
 
@@ -239,12 +244,10 @@ class CondensedScoreEngine:
             enc = C.byref(mem["enc"])
             L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab0), enc, 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea1),
                                        self.math, s), "tsd_edge_embed")
-            h_in = mem["z"]
-            for blk in mem["blocks"]:
-                L.check(lib.tsd_cfconv_layer(b, e, L.ptr(ea1), C.byref(blk), L.ptr(h_in), L.ptr(hbuf), L.ptr(ef0),
-                                             L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2), self.math, s),
-                        "tsd_cfconv_layer")
-                h_in = hbuf
+            L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
+                                           L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
+                                           self.math, s), "tsd_schnet_encoder")
+            h_in = hbuf
             if self.two_graphs:
                 L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea2),
                                            self.math, s), "tsd_edge_embed")
@@ -298,7 +301,7 @@ class DualScoreEngine:
                                                     model.edge_cat_global if self.ts else None, cat_act, self.wv)
         self.enc_l, self._k2 = _edge_encoder_struct(model.edge_encoder_local, act,
                                                     model.edge_cat_local if self.ts else None, cat_act, self.wv)
-        self.blocks = [_interaction_struct(b, self.wv) for b in model.encoder_global.interactions]
+        self.blocks = _interaction_array([_interaction_struct(b, self.wv) for b in model.encoder_global.interactions])
         n_local = len(model.encoder_local.convs)
         self.gines = [_gine_struct(c, i < n_local - 1, self.wv) for i, c in enumerate(model.encoder_local.convs)]
         self.pair_g = _pair_mlp_struct(model.grad_global_dist_mlp, self.wv)
@@ -331,12 +334,10 @@ class DualScoreEngine:
         # global: edge encoder -> SchNet -> pair MLP on every edge
         L.check(lib.tsd_edge_embed(b, e, codes, C.byref(self.enc_g), 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea_g),
                                    self.math, s), "tsd_edge_embed")
-        h_in = self.h0_global
-        for blk in self.blocks:
-            L.check(lib.tsd_cfconv_layer(b, e, L.ptr(ea_g), C.byref(blk), L.ptr(h_in), L.ptr(hbuf), L.ptr(ef0),
-                                         L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2), self.math, s),
-                    "tsd_cfconv_layer")
-            h_in = hbuf
+        L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea_g), self.blocks, len(self.blocks), L.ptr(self.h0_global),
+                                       L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
+                                       self.math, s), "tsd_schnet_encoder")
+        h_in = hbuf
         L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
                                  L.ptr(self.edge_inv_global), self.math, s), "tsd_pair_mlp")
         # local: edge encoder on all edges, GIN + pair MLP restricted to type > 0 by masks
