@@ -231,29 +231,42 @@ def api_call(args, model, data_host, device):
     return pos.cpu(), traj
 
 
+def committed_traffic():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the top kernels, from
+    the committed `ncu --set full` capture (profiles/r1_ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
 def kernel_rooflines(args, eng, peaks, device):
-    """Live CUDA-event timing of the two kernels that matter, on the engine's current edge
-    list: the per-edge linear layer (dominant: >95% of the FLOPs) and the CFConv segmented
-    aggregation (the HBM-bound message-passing kernel)."""
+    """Live CUDA-event timing (kernel alone, L2 flushed) of the two kernels that matter, on the
+    engine's current late-trajectory edge list:
+      * the dominant kernel: the fused filter network of one CFConv layer (two chained
+        E x H x H tensor-core GEMMs; the same kernel also runs the node update) -> tensor roofline
+      * the CFConv segmented aggregation (the HBM-bound message-passing kernel) -> HBM roofline."""
     from tsdiff_b200 import _lib as L
     lib = L.load()
     plan, h = eng.plan, eng.hidden
     e = plan.edge_count()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    x = torch.randn(max(plan.edge_capacity, 1), h, device=device)
-    out = torch.empty_like(x)
-    w = torch.randn(h, h, device=device) / h ** 0.5
-    b = torch.zeros(h, device=device)
-    lin = L.linear(w, b)
+    # L2 flush = write pass + read pass over 256 MiB each: the read pass evicts the dirty lines of
+    # the write pass, so their write-back does not compete with the timed kernel
+    flush_w = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    flush_r = torch.zeros(64 << 20, dtype=torch.float32, device=device)
+    ws = eng.ws
+    x = ws.edge[2]  # edge_attr of the last evaluation (E_cap, H)
+    tmp, out = ws.edge[4], ws.edge[5]
+    blocks = eng.members[0]["blocks"] if hasattr(eng, "members") else eng.blocks
     math = L.MATH[args.math]
+    traffic = committed_traffic()
 
     def timed(fn, reps=10):
         ts = []
         for _ in range(3):
             fn()
         for _ in range(reps):
-            flush_l2(flush)
+            flush_w.zero_()
+            flush_r.sum()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
             fn()
@@ -262,21 +275,26 @@ def kernel_rooflines(args, eng, peaks, device):
             ts.append(t0.elapsed_time(t1) * 1e-3)
         return sum(ts) / len(ts)
 
-    t_lin = timed(lambda: L.check(lib.tsd_linear(plan.edge_capacity, L.ptr(plan.num_edges), L.ptr(x), C.byref(lin),
-                                                 L.ACT["ssp"], L.ptr(out), math, stream), "tsd_linear"))
-    flops = 2.0 * e * h * h
-    tensor = {"bound": "tensor", "kernel": "per-edge linear layer E x %d x %d (%s)" % (h, h, args.math),
-              "achieved": flops / t_lin / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
-              "frac": flops / t_lin / 1e12 / peaks["tensor_burst"], "traffic": None,
-              "peak_source": peaks["source"] + " bf16 burst", "us_per_launch": t_lin * 1e6, "rows": e}
-    x1 = torch.randn(max(plan.num_nodes, 1), h, device=device)
-    agg = torch.empty_like(x1)
+    t_f = timed(lambda: L.check(lib.tsd_filter_network(C.byref(plan.c_batch), C.byref(plan.c_edges), L.ptr(x),
+                                                       C.byref(blocks[0]), L.ptr(tmp), L.ptr(out), math, stream),
+                                "tsd_filter_network"))
+    flops = 2 * 2.0 * e * h * h
+    kname = "k_chain_tf32" if args.math == "tf32" else "k_gemm_ffma"
+    tensor = {"bound": "tensor", "kernel": "%s: CFConv filter network nn2(ssp(nn0(edge_attr)))*C, 2 x (E x %d x %d), %s"
+                                           % (kname, h, h, args.math),
+              "achieved": flops / t_f / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
+              "frac": flops / t_f / 1e12 / peaks["tensor_burst"], "traffic": traffic.get(kname),
+              "peak_source": peaks["source"] + " bf16 burst (tf32 tensor peak is half of it)",
+              "us_per_launch": t_f * 1e6, "rows": e, "algorithmic_flops": flops,
+              "algorithmic_bytes": 2 * e * h * 4 + 2 * h * h * 4}
+    x1 = ws.node[1]
+    agg = ws.node[2]
     t_agg = timed(lambda: L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_batch), C.byref(plan.c_edges), h, L.ptr(x1),
-                                                           L.ptr(x), L.ptr(agg), stream), "tsd_cfconv_aggregate"))
+                                                           L.ptr(out), L.ptr(agg), stream), "tsd_cfconv_aggregate"))
     n = plan.num_nodes
     nbytes = e * h * 4 + 2 * n * h * 4 + e * 8 + (n + 1) * 4
     hbm = {"bound": "hbm", "kernel": "k_cfconv_aggregate", "achieved": nbytes / t_agg / 1e9, "peak": peaks["hbm"],
-           "unit": "GB/s", "frac": nbytes / t_agg / 1e9 / peaks["hbm"], "traffic": None,
+           "unit": "GB/s", "frac": nbytes / t_agg / 1e9 / peaks["hbm"], "traffic": traffic.get("k_cfconv_aggregate"),
            "peak_source": peaks["source"], "us_per_launch": t_agg * 1e6, "algorithmic_bytes": nbytes}
     return tensor, hbm
 

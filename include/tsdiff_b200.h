@@ -163,6 +163,11 @@ int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const f
                      float* ef1, float* nf0, float* nf1, float* nf2, int32_t math,
                      tsd_stream_t stream);
 
+/* The filter network of one CFConv on its own (models/encoder/schnet.py:91-98):
+ * filt = nn2(ssp(nn0(edge_attr))) * C(len).  tmp is (E_cap, H) scratch (fp32 mode only). */
+int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                       const tsd_interaction_t* blk, float* tmp, float* filt, int32_t math, tsd_stream_t stream);
+
 /* The whole SchNet encoder (models/encoder/schnet.py:203-225): `num_blocks` interaction blocks
  * applied in sequence, h_out = SchNet(h_in).  Same scratch as tsd_cfconv_layer.  In tf32 mode the
  * blocks run as chained tensor-core kernels (filter network fused on the edges; lin2 -> lin ->

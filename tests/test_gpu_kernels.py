@@ -344,3 +344,28 @@ def test_cfconv_aggregate_bit_exact_vs_sequential_scatter(syn4):
                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "aggregate")
     ref = tp.scatter_add(x1[idx[0]] * filt[:e], idx[1], dim=0, dim_size=n)
     assert torch.equal(agg.cpu(), ref)
+
+
+def test_stress_shape_forward_vs_oracle():
+    """BASELINE config 5 shape at reduced count: ~60-atom reactions, cutoff enlarged to 15 A so the
+    32-neighbour cap binds (asymmetric radius graph).  Full path-B forward vs the oracle."""
+    from tsdiff_b200.config import AttrDict
+    cfg = AttrDict(dict(TRAIN_CONFIG_MODEL))
+    cfg.edge_cutoff = 15.0
+    cfg.encoder = AttrDict(dict(TRAIN_CONFIG_MODEL.encoder))
+    cfg.encoder.cutoff = 15.0
+    from tsdiff_b200.models.epsnet import get_model
+    torch.manual_seed(0)
+    m = get_model(cfg).to(DEV)
+    g = make_batch(6, seed=21, min_atoms=55, max_atoms=65)
+    d = to_dev(g, DEV)
+    torch.manual_seed(6)
+    pos = torch.randn(g["atom_type"].numel(), 3) * 4.0
+    ei, idx, ln = m(d["atom_type"], d["r_feat"], d["p_feat"], pos.to(DEV), d["bond_index"], d["bond_type"], d["batch"], None)
+    rei, ridx, rln = O.condensenc_forward(oracle_params(m), cfg, g["atom_type"], g["r_feat"], g["p_feat"], pos,
+                                          g["bond_index"], g["bond_type"], g["batch"])
+    assert torch.equal(idx.cpu(), ridx) and torch.equal(ln.cpu(), rln)
+    n = g["atom_type"].numel()
+    keys = set((ridx[0] * n + ridx[1]).tolist())
+    assert any((int(c) * n + int(r)) not in keys for r, c in ridx.t().tolist()), "cap should make the graph asymmetric"
+    assert rel_err(ei, rei) < EPS_TOL and max_rel_err(ei, rei) < EPS_TOL

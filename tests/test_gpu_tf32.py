@@ -128,3 +128,20 @@ def test_condensenc_forward_tf32_batch100_chained_kernels():
     assert torch.equal(out["tf32"][1], out["fp32"][1]) and torch.equal(out["tf32"][2], out["fp32"][2])
     err = rel_err(out["tf32"][0], out["fp32"][0])
     assert 1e-7 < err < 3e-3, err
+
+
+def test_dualenc_forward_tf32_batch100():
+    """Path A at config-2 size (H = 128 chained kernels + GIN layers): tf32 vs fp32 FFMA path."""
+    from tsdiff_b200.synthetic import make_batch
+    g = make_batch(100, seed=2)
+    m = make_model("dualenc", 0, DEV)
+    d = to_dev(g, DEV)
+    pos = (g["pos_init"] * 4.0).to(DEV)
+    out = {}
+    for math in ("fp32", "tf32"):
+        m.math = math
+        out[math] = m(d["atom_type"], pos, d["bond_index"], d["bond_type"], d["batch"], None, return_edges=True)
+    assert torch.equal(out["tf32"][2], out["fp32"][2]) and torch.equal(out["tf32"][3], out["fp32"][3])
+    for k in (0, 1):  # edge_inv_global, edge_inv_local
+        err = rel_err(out["tf32"][k], out["fp32"][k])
+        assert 1e-7 < err < 5e-3, (k, err)

@@ -255,6 +255,46 @@ static ChainStage chain_stage(const tsd_linear_t& lin, int act) {
   return st;
 }
 
+// Filter network of one CFConv on its own (schnet.py:91-98): filt = nn2(ssp(nn0(edge_attr))) * C(len).
+// tf32 mode: one chained tensor-core kernel; fp32 mode: two FFMA GEMMs through `tmp`.
+extern "C" int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                                  const tsd_interaction_t* blk, float* tmp, float* filt, int32_t math,
+                                  tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && edge_attr && blk && tmp && filt);
+  cudaStream_t s = tsd_cu(stream);
+  const int H = blk->nn2.out_features;
+  if (math == TSD_MATH_TF32 && (H == 128 || H == 256) && blk->nn0.in_features == H && blk->nn0.out_features == H &&
+      blk->nn2.in_features == H && batch->edge_capacity >= 1024) {
+    ChainArgs c;
+    memset(&c, 0, sizeof(c));
+    c.M_cap = batch->edge_capacity;
+    c.M_ptr = edges->num_edges;
+    c.H = H;
+    c.A = edge_attr;
+    c.num_stages = 2;
+    c.st[0] = chain_stage(blk->nn0, TSD_ACT_SSP);
+    c.st[1] = chain_stage(blk->nn2, TSD_ACT_NONE);
+    c.st[1].scale_len = edges->length;
+    c.st[1].cutoff = blk->cutoff;
+    c.st[1].smooth = blk->smooth;
+    c.st[1].store = filt;
+    return tsd_chain_tf32(c, s);
+  }
+  GemmArgs g = edge_gemm(batch, edges, blk->nn0);
+  g.A = edge_attr;
+  g.act = TSD_ACT_SSP;
+  g.C = tmp;
+  g.round_out = 1;
+  TSD_TRY(tsd_gemm(g, math, s));
+  g = edge_gemm(batch, edges, blk->nn2);
+  g.A = tmp;
+  g.scale_len = edges->length;
+  g.cutoff = blk->cutoff;
+  g.smooth = blk->smooth;
+  g.C = filt;
+  return tsd_gemm(g, math, s);
+}
+
 // Whole SchNet encoder (schnet.py:203-225).  fp32 mode: one tsd_cfconv_layer per block.  tf32
 // mode: per block ONE chained filter-network kernel on the edges, the segmented aggregation, and
 // ONE chained node kernel that also produces the next block's x1 = lin1(h') -- 3 launches per

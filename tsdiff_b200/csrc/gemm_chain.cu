@@ -12,7 +12,7 @@
 //              (schnet.py:91-98; saves the (E,H) intermediate's round trip), and
 //          (b) the node update            h' = h + lin(ssp(lin2(agg))),  x1' = lin1_next(h')
 //              (schnet.py:103-104,124-128 + the next block's :101; 3 launches -> 1).
-// Shared memory: abuf H/32 panels x 16 KiB + ring 2 x (16 KiB + H*128 B) (224 KiB at H = 256);
+// Shared memory: abuf H/32 panels x 16 KiB + ring of 3 W panels (H*128 B each): 224 KiB at H = 256;
 // TMEM: two H-column accumulators used alternately.  One CTA per SM.
 #include <stdio.h>
 #include <stdlib.h>
@@ -24,7 +24,7 @@
 namespace {
 using namespace tc;
 
-constexpr int CH_RING = 2;
+constexpr int CH_RING = 3;  // W-panel slots; the A operand of every stage lives in abuf
 constexpr int CH_THREADS = 512;  // 16 warps: the epilogues are latency bound, 4 warps per TMEM lane quarter
 
 // One stage's epilogue.  VIA_TILE: the result (plus residual) goes to global memory and/or the
@@ -129,10 +129,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_tf32(const ChainArgs p,
   const int H = p.H, ns = p.num_stages;
   const int num_kb = H / TC_BK;
   const uint32_t w_panel_bytes = (uint32_t)H * TC_BK * 4;
-  const uint32_t slot_bytes = TC_A_PANEL_BYTES + w_panel_bytes;
+  const uint32_t slot_bytes = w_panel_bytes;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  // layout: [abuf: num_kb panels][ring: CH_RING slots of (A panel, W panel)]
+  // layout: [abuf: num_kb A panels (stage 0: loaded by TMA; later stages: written by the epilogue)]
+  //         [ring: CH_RING slots of one W panel]
   uint8_t* abuf = smem_gen;
   const uint32_t abuf_bytes = (uint32_t)num_kb * TC_A_PANEL_BYTES;
   uint8_t* ring = smem_gen + abuf_bytes;
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_tf32(const ChainArgs p,
     if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));
     uint8_t* slot = ring + (size_t)s * slot_bytes;
     mbar_arrive_expect_tx(&bar_full[s], w_panel_bytes + (stage == 0 ? TC_A_PANEL_BYTES : 0));
-    if (stage == 0) tma_load_2d(slot, &maps.a, &bar_full[s], kb * TC_BK, m0);
-    tma_load_2d(slot + TC_A_PANEL_BYTES, &maps.w[stage], &bar_full[s], kb * TC_BK, 0);
+    if (stage == 0) tma_load_2d(abuf + (size_t)kb * TC_A_PANEL_BYTES, &maps.a, &bar_full[s], kb * TC_BK, m0);
+    tma_load_2d(slot, &maps.w[stage], &bar_full[s], kb * TC_BK, 0);
   };
 
 #pragma unroll
@@ -191,8 +192,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_tf32(const ChainArgs p,
         mbar_wait(&bar_full[s], (uint32_t)(round & 1));
         tc_fence_after();
         const uint32_t slot = ring_base + (uint32_t)s * slot_bytes;
-        const uint64_t adesc = umma_desc_sw128(stage == 0 ? slot : smem_base + (uint32_t)kb * TC_A_PANEL_BYTES);
-        const uint64_t bdesc = umma_desc_sw128(slot + TC_A_PANEL_BYTES);
+        const uint64_t adesc = umma_desc_sw128(smem_base + (uint32_t)kb * TC_A_PANEL_BYTES);
+        const uint64_t bdesc = umma_desc_sw128(slot);
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 8; ++kk)
           umma_tf32(acc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
@@ -248,7 +249,7 @@ int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream) {
     if (!make_tensor_map(&maps.w[s], w, (uint64_t)c.H, (uint64_t)c.H, (uint32_t)c.H)) return TSD_ERR_UNSUPPORTED;
   }
   const int num_kb = c.H / TC_BK;
-  size_t ring_bytes = (size_t)CH_RING * (TC_A_PANEL_BYTES + (size_t)c.H * TC_BK * 4);
+  size_t ring_bytes = (size_t)CH_RING * ((size_t)c.H * TC_BK * 4);
   const size_t tile_bytes = (size_t)(CH_THREADS / 32) * 32 * 36 * sizeof(float);  // epilogue transpose tiles live in the ring
   if (ring_bytes < tile_bytes) ring_bytes = tile_bytes;
   const size_t smem = (size_t)num_kb * TC_A_PANEL_BYTES + ring_bytes + 1024;
