@@ -1,6 +1,7 @@
 // C-ABI entry points that compose the kernels into the reference's operator granularity
 // (edge embedding, one SchNet interaction, one GINE conv, the output MLP).  See
 // include/tsdiff_b200.h for the contract and the reference lines each call replaces.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -8,6 +9,9 @@
 
 int tsd_launch_cfconv_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
                                 const float* x1, const float* filt, float* agg, cudaStream_t s);
+int tsd_launch_cfconv_aggregate_staged(const tsd_batch_t* b, int H, const int* in_ptr, const int* in_eid,
+                                       const int* in_src, const float* x1, const float* filt, float* agg,
+                                       cudaStream_t s);
 int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
                               const int* local_tab, const float* h, const float* ea, const float* eps, float* out,
                               cudaStream_t s);
@@ -242,6 +246,13 @@ extern "C" int tsd_linear(int32_t rows, const int32_t* rows_dev, const float* x,
 extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t channels,
                                     const float* x1, const float* filt, float* agg, tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && x1 && filt && agg);
+  // TSD_AGG_VARIANT=5 selects the graph-staged kernel (x1 rows in shared memory).  It was measured
+  // SLOWER than the node-parallel kernel at batch 100 (30 us vs 18 us warm at E = 33.5k: only
+  // G x H/128 CTAs, too little memory-level parallelism), so it is kept for experiments only.
+  const char* v = getenv("TSD_AGG_VARIANT");
+  if (v && atoi(v) == 5)
+    return tsd_launch_cfconv_aggregate_staged(batch, channels, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt, agg,
+                                              tsd_cu(stream));
   return tsd_launch_cfconv_aggregate(batch->num_nodes, channels, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt,
                                      agg, tsd_cu(stream));
 }

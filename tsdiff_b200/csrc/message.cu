@@ -5,6 +5,8 @@
 // The in-CSR lists the edges of every target in ascending source order, which is the order
 // a sequential scatter_add over the row-major sorted edge list visits them, so sums are
 // reproducible run to run and match the oracle's association order.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // HBM-bound: per target node stream its in-edges' filter rows (E*H*4 bytes in total, each
@@ -65,14 +67,100 @@ __global__ void __launch_bounds__(256) k_cfconv_aggregate(int num_nodes, int H, 
   if (active) *reinterpret_cast<float4*>(agg + (size_t)node * H + off) = acc;
 }
 
+// Graph-staged variant (default): one CTA per (reaction, 128-channel slab).  The x1 rows of the
+// reaction (<= 256 x 512 B) are staged in shared memory once, so the per-edge gather of the
+// source features never leaves the SM; only the filter rows stream from L2/HBM, each exactly
+// once.  (The node-parallel kernel above re-reads a 512-byte x1 slab per edge from L2: E*H*4
+// bytes of gather traffic on top of the E*H*4 filter stream.)
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_cfconv_aggregate_staged(int H, const int* __restrict__ graph_ptr,
+                                                                 const int* __restrict__ in_ptr,
+                                                                 const int* __restrict__ in_eid,
+                                                                 const int* __restrict__ in_src,
+                                                                 const float* __restrict__ x1,
+                                                                 const float* __restrict__ filt, float* __restrict__ agg) {
+  extern __shared__ float4 sx[];  // [n][32] float4 = this slab of the reaction's x1 rows
+  const int g = blockIdx.x, slab = blockIdx.y;
+  const int n0 = graph_ptr[g], n = graph_ptr[g + 1] - n0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int off = slab * 128 + lane * 4;
+  const bool active = off < H;
+  for (int i = warp; i < n; i += nwarps)
+    sx[i * 32 + lane] = active ? __ldg(reinterpret_cast<const float4*>(x1 + (size_t)(n0 + i) * H + off))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int i = warp; i < n; i += nwarps) {
+    const int node = n0 + i;
+    const int beg = in_ptr[node], end = in_ptr[node + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      const int e_l = lane < cnt ? in_eid[base + lane] : 0;
+      const int r_l = lane < cnt ? in_src[base + lane] - n0 : 0;
+      int j = 0;
+      for (; j + UNROLL <= cnt; j += UNROLL) {
+        float4 w[UNROLL];
+        int r[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int e = __shfl_sync(TSD_FULL_MASK, e_l, j + u);
+          r[u] = __shfl_sync(TSD_FULL_MASK, r_l, j + u);
+          if (active) w[u] = __ldcs(reinterpret_cast<const float4*>(filt + (size_t)e * H + off));  // streamed once
+        }
+        if (active) {
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) tsd_fma_rn4(acc, sx[r[u] * 32 + lane], w[u]);
+        }
+      }
+      for (; j < cnt; ++j) {
+        const int e = __shfl_sync(TSD_FULL_MASK, e_l, j), r = __shfl_sync(TSD_FULL_MASK, r_l, j);
+        if (active) tsd_fma_rn4(acc, sx[r * 32 + lane], __ldcs(reinterpret_cast<const float4*>(filt + (size_t)e * H + off)));
+      }
+    }
+    if (active) *reinterpret_cast<float4*>(agg + (size_t)node * H + off) = acc;
+  }
+}
+
+int tsd_launch_cfconv_aggregate_staged(const tsd_batch_t* b, int H, const int* in_ptr, const int* in_eid,
+                                       const int* in_src, const float* x1, const float* filt, float* agg,
+                                       cudaStream_t s) {
+  TSD_REQUIRE(H % 4 == 0 && H >= 4 && H <= 4096);
+  if (b->num_graphs == 0) return TSD_OK;
+  const int slabs = tsd_ceil_div(H, 128);
+  const size_t smem = (size_t)b->max_graph_nodes * 32 * sizeof(float4);
+  if (smem > 48 * 1024) TSD_CUDA(cudaFuncSetAttribute(k_cfconv_aggregate_staged<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cfconv_aggregate_staged<8><<<dim3(b->num_graphs, slabs), 256, smem, s>>>(H, b->graph_ptr, in_ptr, in_eid, in_src, x1, filt, agg);
+  TSD_LAUNCH_CHECK();
+  return TSD_OK;
+}
+
 int tsd_launch_cfconv_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* in_src,
                                 const float* x1, const float* filt, float* agg, cudaStream_t s) {
   TSD_REQUIRE(H % 4 == 0 && H >= 4 && H <= 4096);
   if (num_nodes == 0) return TSD_OK;
   const int slabs = tsd_ceil_div(H, 128);
   const long long warps = (long long)num_nodes * slabs;
-  k_cfconv_aggregate<8><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1,
-                                                                    filt, agg);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("TSD_AGG_VARIANT");
+    variant = e ? atoi(e) : 2;  // measured best at batch 100: UNROLL 4, 60 registers, 256 threads
+  }
+  switch (variant) {
+    case 1:
+      k_cfconv_aggregate<4><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
+      break;
+    case 2:
+      k_cfconv_aggregate<4><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
+      break;
+    case 3:
+      k_cfconv_aggregate<8><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
+      break;
+    case 4:
+      k_cfconv_aggregate<16><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
+      break;
+    default:
+      k_cfconv_aggregate<8><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
+  }
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }
