@@ -257,6 +257,28 @@ extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t*
                                      agg, tsd_cu(stream));
 }
 
+// library-owned side stream + events for the fork/join inside tsd_schnet_encoder
+struct EncoderFork {
+  static const int MAX_BLOCKS = 32;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t edge_done[MAX_BLOCKS], agg_done[MAX_BLOCKS];
+  bool ready = false;
+  int init(int num_blocks) {
+    if (num_blocks > MAX_BLOCKS) return TSD_ERR_UNSUPPORTED;
+    if (ready) return TSD_OK;
+    TSD_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    TSD_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    TSD_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_BLOCKS; ++i) {
+      TSD_CUDA(cudaEventCreateWithFlags(&edge_done[i], cudaEventDisableTiming));
+      TSD_CUDA(cudaEventCreateWithFlags(&agg_done[i], cudaEventDisableTiming));
+    }
+    ready = true;
+    return TSD_OK;
+  }
+};
+
 static ChainStage chain_stage(const tsd_linear_t& lin, int act) {
   ChainStage st;
   memset(&st, 0, sizeof(st));
@@ -333,15 +355,28 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     }
     return TSD_OK;
   }
-  // x1 of block 0
-  GemmArgs g = node_gemm(batch, blocks[0].lin1);
+  // The filter networks depend only on edge_attr, not on h: block l+1's edge kernel can run while
+  // block l's aggregation / node update is in flight.  Fork a side stream for the node-side chain
+  // (x1_0, agg_l, node kernel_l); the main stream runs the edge kernels back to back, alternating
+  // between two filter buffers.  The edge kernel's second wave leaves most SMs idle (188-263 tiles
+  // on 148 SMs), which is where the 15-CTA node kernels and the aggregation execute.  Inside a
+  // CUDA-graph capture the event waits become graph edges.
+  static EncoderFork fk;
+  TSD_TRY(fk.init(num_blocks));
+  cudaStream_t side = fk.side;
+  TSD_CUDA(cudaEventRecord(fk.fork, s));
+  TSD_CUDA(cudaStreamWaitEvent(side, fk.fork, 0));
+  GemmArgs g = node_gemm(batch, blocks[0].lin1);  // x1 of block 0
   g.A = h_in;
   g.C = nf0;
-  TSD_TRY(tsd_gemm(g, math, s));
+  TSD_TRY(tsd_gemm(g, math, side));
   const float* h = h_in;
+  float* filt_buf[2] = {ef1, ef0};
   for (int l = 0; l < num_blocks; ++l) {
     const tsd_interaction_t& b = blocks[l];
-    // filter network on the edges: ef1 = nn2(ssp(nn0(edge_attr))) * C(len)
+    float* filt = filt_buf[l & 1];
+    if (l >= 2) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - 2], 0));  // buffer reuse: agg_{l-2} has read it
+    // filter network on the edges: filt = nn2(ssp(nn0(edge_attr))) * C(len)
     ChainArgs c;
     memset(&c, 0, sizeof(c));
     c.M_cap = batch->edge_capacity;
@@ -354,9 +389,13 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     c.st[1].scale_len = edges->length;
     c.st[1].cutoff = b.cutoff;
     c.st[1].smooth = b.smooth;
-    c.st[1].store = ef1;
+    c.st[1].store = filt;
     TSD_TRY(tsd_chain_tf32(c, s));
-    TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, nf0, ef1, nf1, s));
+    TSD_CUDA(cudaEventRecord(fk.edge_done[l], s));
+    TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
+    TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, nf0, filt, nf1,
+                                        side));
+    TSD_CUDA(cudaEventRecord(fk.agg_done[l], side));
     // node update: h' = h + lin(ssp(lin2(agg))) and, unless this is the last block, x1' = lin1_next(h')
     memset(&c, 0, sizeof(c));
     c.M_cap = batch->num_nodes;
@@ -373,8 +412,10 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     } else {
       c.num_stages = 2;
     }
-    TSD_TRY(tsd_chain_tf32(c, s));
+    TSD_TRY(tsd_chain_tf32(c, side));
     h = h_out;
   }
+  TSD_CUDA(cudaEventRecord(fk.join, side));
+  TSD_CUDA(cudaStreamWaitEvent(s, fk.join, 0));
   return TSD_OK;
 }
