@@ -211,8 +211,9 @@ class CondensedScoreEngine:
         h = int(cfg.hidden_dim)
         self.hidden = h
         self.cutoff = float(cfg.edge_cutoff)
-        # d_emb, tmp, ea1, ea2, ef0, ef1
-        self.ws = _Scratch(plan, h, 6, 4)
+        # d_emb, tmp, ea1, ea2, ef0, ef1, tmp2
+        self.ws = _Scratch(plan, h, 7, 4)
+        self.side = torch.cuda.Stream(device=plan.device)  # second-graph edge embedding runs beside the encoder
         self.edge_inv = torch.zeros(max(plan.edge_capacity, 1), dtype=torch.float32, device=plan.device)
         atom_type = atom_type.to(torch.long).contiguous()
         r_feat = r_feat.to(torch.long).contiguous()
@@ -237,24 +238,30 @@ class CondensedScoreEngine:
         lib = L.load()
         plan, ws, s = self.plan, self.ws, _stream()
         b, e = C.byref(plan.c_batch), C.byref(plan.c_edges)
-        d_emb, tmp, ea1, ea2, ef0, ef1 = ws.edge
+        d_emb, tmp, ea1, ea2, ef0, ef1, tmp2 = ws.edge
         hbuf, nf0, nf1, nf2 = ws.node
         plan.build_edges(pos, self.cutoff)
+        main = torch.cuda.current_stream()
         for mi, mem in enumerate(self.members):
             enc = C.byref(mem["enc"])
             L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab0), enc, 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea1),
                                        self.math, s), "tsd_edge_embed")
-            L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
-                                           L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                           self.math, s), "tsd_schnet_encoder")
-            h_in = hbuf
             if self.two_graphs:
-                L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea2),
-                                           self.math, s), "tsd_edge_embed")
+                # the pred_edge_order graph's edge embedding only needs d_emb: fork it onto a side
+                # stream (a graph branch under capture) so it fills the SMs the encoder leaves idle
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp2), L.ptr(ea2),
+                                               self.math, _stream()), "tsd_edge_embed")
                 ea_out = ea2
             else:
                 ea_out = ea1
-            L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_out), C.byref(mem["pair"]), 1 if mi > 0 else 0,
+            L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
+                                           L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
+                                           self.math, s), "tsd_schnet_encoder")
+            if self.two_graphs:
+                main.wait_stream(self.side)
+            L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_out), C.byref(mem["pair"]), 1 if mi > 0 else 0,
                                      L.ptr(ef0), L.ptr(self.edge_inv), self.math, s), "tsd_pair_mlp")
 
     def score_channels(self, clip):
@@ -289,8 +296,12 @@ class DualScoreEngine:
         h = int(cfg.hidden_dim)
         self.hidden = h
         self.cutoff = float(cfg.cutoff)
-        self.ws = _Scratch(plan, h, 6, 5)
+        self.ws = _Scratch(plan, h, 7, 7)
+        self.side = torch.cuda.Stream(device=plan.device)  # the local (GIN) branch runs beside the global one
         cap = max(plan.edge_capacity, 1)
+        # TS variant (edge_cat): the local edge encoder needs its own d_emb / tmp scratch
+        self.local_scratch = ([torch.empty(cap, h, dtype=torch.float32, device=plan.device) for _ in range(2)]
+                              if self.ts else [None, None])
         self.edge_inv_global = torch.zeros(cap, dtype=torch.float32, device=plan.device)
         self.edge_inv_local = torch.zeros(cap, dtype=torch.float32, device=plan.device)
         self.atom_type = atom_type.to(torch.long).contiguous()
@@ -327,29 +338,34 @@ class DualScoreEngine:
         lib = L.load()
         plan, ws, s = self.plan, self.ws, _stream()
         b, e = C.byref(plan.c_batch), C.byref(plan.c_edges)
-        d_emb, tmp, ea_g, ea_l, ef0, ef1 = ws.edge
-        hbuf, nf0, nf1, nf2, hloc = ws.node
+        d_emb, tmp, ea_g, ea_l, ef0, ef1, efl = ws.edge
+        hbuf, nf0, nf1, nf2, hloc, nf0l, nf1l = ws.node
         plan.build_edges(pos, self.cutoff)
         codes = L.ptr(plan.tab1)
+        main = torch.cuda.current_stream()
+        # local branch (independent of the global one) on the side stream: edge encoder on all edges,
+        # GIN + pair MLP restricted to type > 0 by masks
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            ss = _stream()
+            L.check(lib.tsd_edge_embed(b, e, codes, C.byref(self.enc_l), 0, L.ptr(self.local_scratch[0]),
+                                       L.ptr(self.local_scratch[1]), L.ptr(ea_l), self.math, ss), "tsd_edge_embed")
+            h_in = self.h0_local
+            for gc in self.gines:
+                L.check(lib.tsd_gine_layer(b, e, L.ptr(ea_l), C.byref(gc), L.ptr(h_in), L.ptr(hloc), L.ptr(nf0l),
+                                           L.ptr(nf1l), self.math, ss), "tsd_gine_layer")
+                h_in = hloc
+            L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_l), C.byref(self.pair_l), 0, L.ptr(efl),
+                                     L.ptr(self.edge_inv_local), self.math, ss), "tsd_pair_mlp")
         # global: edge encoder -> SchNet -> pair MLP on every edge
         L.check(lib.tsd_edge_embed(b, e, codes, C.byref(self.enc_g), 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea_g),
                                    self.math, s), "tsd_edge_embed")
         L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea_g), self.blocks, len(self.blocks), L.ptr(self.h0_global),
                                        L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
                                        self.math, s), "tsd_schnet_encoder")
-        h_in = hbuf
-        L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
+        L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
                                  L.ptr(self.edge_inv_global), self.math, s), "tsd_pair_mlp")
-        # local: edge encoder on all edges, GIN + pair MLP restricted to type > 0 by masks
-        L.check(lib.tsd_edge_embed(b, e, codes, C.byref(self.enc_l), 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea_l),
-                                   self.math, s), "tsd_edge_embed")
-        h_in = self.h0_local
-        for gc in self.gines:
-            L.check(lib.tsd_gine_layer(b, e, L.ptr(ea_l), C.byref(gc), L.ptr(h_in), L.ptr(hloc), L.ptr(nf0),
-                                       L.ptr(nf1), self.math, s), "tsd_gine_layer")
-            h_in = hloc
-        L.check(lib.tsd_pair_mlp(b, e, L.ptr(h_in), L.ptr(ea_l), C.byref(self.pair_l), 0, L.ptr(ef0),
-                                 L.ptr(self.edge_inv_local), self.math, s), "tsd_pair_mlp")
+        main.wait_stream(self.side)
 
     def score_channels(self, clip, clip_local, w_global):
         """dualenc.py:827-849: local score on type > 0 edges (+ optional clip_local); global
