@@ -171,11 +171,14 @@ int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* edges, const
 /* The whole SchNet encoder (models/encoder/schnet.py:203-225): `num_blocks` interaction blocks
  * applied in sequence, h_out = SchNet(h_in).  Same scratch as tsd_cfconv_layer.  In tf32 mode the
  * blocks run as chained tensor-core kernels (filter network fused on the edges; lin2 -> lin ->
- * next block's lin1 fused on the nodes). h_in is not modified; h_out may not alias h_in. */
+ * next block's lin1 fused on the nodes) and the edge kernels of different blocks overlap with each
+ * other and with the node side on library-owned side streams (graph branches under capture).
+ * filt_pool (optional): filt_pool_count x (E_cap, H) buffers so every block owns its filter buffer.
+ * h_in is not modified; h_out may not alias h_in. */
 int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                        const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
-                       float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, int32_t math,
-                       tsd_stream_t stream);
+                       float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* filt_pool,
+                       int32_t filt_pool_count, int32_t math, tsd_stream_t stream);
 
 /* The two building blocks of K4, exposed on their own for unit tests and for the per-kernel
  * roofline timing in bench.py:

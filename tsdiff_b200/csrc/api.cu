@@ -260,20 +260,29 @@ extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t*
 // library-owned side stream + events for the fork/join inside tsd_schnet_encoder
 struct EncoderFork {
   static const int MAX_BLOCKS = 32;
-  cudaStream_t side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t side = nullptr, edge2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
   cudaEvent_t edge_done[MAX_BLOCKS], agg_done[MAX_BLOCKS];
   bool ready = false;
+  bool two_edge_streams = false;
   int init(int num_blocks) {
     if (num_blocks > MAX_BLOCKS) return TSD_ERR_UNSUPPORTED;
     if (ready) return TSD_OK;
-    TSD_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    // the node-side chain is serial and short (15-CTA kernels): give it the highest priority so its
+    // CTAs are scheduled as soon as an SM frees up instead of queueing behind the edge tiles
+    int prio_lo = 0, prio_hi = 0;
+    TSD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    TSD_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+    TSD_CUDA(cudaStreamCreateWithFlags(&edge2, cudaStreamNonBlocking));
+    TSD_CUDA(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
     TSD_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     TSD_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
     for (int i = 0; i < MAX_BLOCKS; ++i) {
       TSD_CUDA(cudaEventCreateWithFlags(&edge_done[i], cudaEventDisableTiming));
       TSD_CUDA(cudaEventCreateWithFlags(&agg_done[i], cudaEventDisableTiming));
     }
+    const char* e = getenv("TSD_ENCODER_EDGE_STREAMS");
+    two_edge_streams = e && atoi(e) == 2;
     ready = true;
     return TSD_OK;
   }
@@ -334,8 +343,8 @@ extern "C" int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* e
 // block instead of 6 and no (E,H) / (N,H) intermediate round trips.
 extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                                   const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
-                                  float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, int32_t math,
-                                  tsd_stream_t stream) {
+                                  float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* filt_pool,
+                                  int32_t filt_pool_count, int32_t math, tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && edge_attr && blocks && num_blocks >= 1 && h_in && h_out && ef0 && ef1 && nf0 && nf1 && nf2);
   cudaStream_t s = tsd_cu(stream);
   const int H = blocks[0].lin.out_features;
@@ -363,20 +372,33 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
   // CUDA-graph capture the event waits become graph edges.
   static EncoderFork fk;
   TSD_TRY(fk.init(num_blocks));
-  cudaStream_t side = fk.side;
+  cudaStream_t side = fk.side, edge2 = fk.edge2;
   TSD_CUDA(cudaEventRecord(fk.fork, s));
   TSD_CUDA(cudaStreamWaitEvent(side, fk.fork, 0));
+  TSD_CUDA(cudaStreamWaitEvent(edge2, fk.fork, 0));
   GemmArgs g = node_gemm(batch, blocks[0].lin1);  // x1 of block 0
   g.A = h_in;
   g.C = nf0;
   TSD_TRY(tsd_gemm(g, math, side));
   const float* h = h_in;
-  float* filt_buf[2] = {ef1, ef0};
+  // filter buffers: a caller-provided pool (one per block: no reuse waits) or the two scratch buffers
+  const int nbuf = (filt_pool && filt_pool_count >= 2) ? (filt_pool_count < num_blocks ? filt_pool_count : num_blocks) : 2;
+  const size_t buf_elems = (size_t)(batch->edge_capacity > 0 ? batch->edge_capacity : 1) * H;
+  auto filt_of = [&](int l) -> float* {
+    if (filt_pool && filt_pool_count >= 2) return filt_pool + (size_t)(l % nbuf) * buf_elems;
+    return (l & 1) ? ef0 : ef1;
+  };
+  // The edge kernels of consecutive blocks are independent of each other too: they alternate
+  // between two streams so block l+1's tiles fill the SMs that block l's second wave leaves idle.
   for (int l = 0; l < num_blocks; ++l) {
     const tsd_interaction_t& b = blocks[l];
-    float* filt = filt_buf[l & 1];
-    if (l >= 2) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - 2], 0));  // buffer reuse: agg_{l-2} has read it
-    // filter network on the edges: filt = nn2(ssp(nn0(edge_attr))) * C(len)
+    float* filt = filt_of(l);
+    // NOTE measured: letting consecutive blocks' edge kernels run concurrently (alternating streams,
+    // one filter buffer per block) was SLOWER (33-36 vs 38.7 samples/s): the queued edge tiles
+    // starve the serial node-side chain even with a high-priority stream.  Edge kernels therefore
+    // stay on the caller's stream; TSD_ENCODER_EDGE_STREAMS=2 re-enables the experiment.
+    cudaStream_t es = (fk.two_edge_streams && (l & 1)) ? edge2 : s;
+    if (l >= nbuf) TSD_CUDA(cudaStreamWaitEvent(es, fk.agg_done[l - nbuf], 0));  // buffer reuse: agg_{l-nbuf} has read it
     ChainArgs c;
     memset(&c, 0, sizeof(c));
     c.M_cap = batch->edge_capacity;
@@ -390,8 +412,10 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     c.st[1].cutoff = b.cutoff;
     c.st[1].smooth = b.smooth;
     c.st[1].store = filt;
-    TSD_TRY(tsd_chain_tf32(c, s));
-    TSD_CUDA(cudaEventRecord(fk.edge_done[l], s));
+    TSD_TRY(tsd_chain_tf32(c, es));
+    TSD_CUDA(cudaEventRecord(fk.edge_done[l], es));
+    // node side of block l (issued in the same loop iteration so that, under stream capture, every
+    // event is recorded in the capture before anything waits on it)
     TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
     TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, nf0, filt, nf1,
                                         side));
@@ -415,6 +439,8 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     TSD_TRY(tsd_chain_tf32(c, side));
     h = h_out;
   }
+  TSD_CUDA(cudaEventRecord(fk.join2, edge2));
+  TSD_CUDA(cudaStreamWaitEvent(s, fk.join2, 0));
   TSD_CUDA(cudaEventRecord(fk.join, side));
   TSD_CUDA(cudaStreamWaitEvent(s, fk.join, 0));
   return TSD_OK;

@@ -136,6 +136,18 @@ class _WeightView:
         return shadow
 
 
+def _filter_pool(plan, hidden, num_blocks, math):
+    """tf32 mode: one (E_cap, H) filter buffer per interaction block, so the blocks' edge kernels
+    can all be in flight without waiting for a buffer (capped at 4 GiB; fewer buffers just add
+    reuse dependencies)."""
+    import os
+    if math != "tf32" or os.environ.get("TSD_ENCODER_EDGE_STREAMS") != "2":
+        return None, 0  # default: two alternating scratch buffers (see tsd_schnet_encoder)
+    per = max(plan.edge_capacity, 1) * hidden * 4
+    count = max(2, min(num_blocks, (4 << 30) // per))
+    return torch.empty(count * max(plan.edge_capacity, 1) * hidden, dtype=torch.float32, device=plan.device), count
+
+
 def _edge_encoder_struct(enc, act, cat=None, cat_act="none", wv=lambda w: w):
     """enc: layers.MLPEdgeEncoder; cat: nn.Sequential(Linear, act, Linear) or None."""
     keep = []
@@ -214,6 +226,7 @@ class CondensedScoreEngine:
         # d_emb, tmp, ea1, ea2, ef0, ef1, tmp2
         self.ws = _Scratch(plan, h, 7, 4)
         self.side = torch.cuda.Stream(device=plan.device)  # second-graph edge embedding runs beside the encoder
+        self.filt_pool, self.filt_pool_count = _filter_pool(plan, h, len(self.models[0].encoder.interactions), math)
         self.edge_inv = torch.zeros(max(plan.edge_capacity, 1), dtype=torch.float32, device=plan.device)
         atom_type = atom_type.to(torch.long).contiguous()
         r_feat = r_feat.to(torch.long).contiguous()
@@ -258,7 +271,8 @@ class CondensedScoreEngine:
                 ea_out = ea1
             L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
                                            L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                           self.math, s), "tsd_schnet_encoder")
+                                           L.ptr(self.filt_pool), self.filt_pool_count, self.math, s),
+                    "tsd_schnet_encoder")
             if self.two_graphs:
                 main.wait_stream(self.side)
             L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_out), C.byref(mem["pair"]), 1 if mi > 0 else 0,
@@ -298,6 +312,7 @@ class DualScoreEngine:
         self.cutoff = float(cfg.cutoff)
         self.ws = _Scratch(plan, h, 7, 7)
         self.side = torch.cuda.Stream(device=plan.device)  # the local (GIN) branch runs beside the global one
+        self.filt_pool, self.filt_pool_count = _filter_pool(plan, h, len(model.encoder_global.interactions), math)
         cap = max(plan.edge_capacity, 1)
         # TS variant (edge_cat): the local edge encoder needs its own d_emb / tmp scratch
         self.local_scratch = ([torch.empty(cap, h, dtype=torch.float32, device=plan.device) for _ in range(2)]
@@ -362,7 +377,7 @@ class DualScoreEngine:
                                    self.math, s), "tsd_edge_embed")
         L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea_g), self.blocks, len(self.blocks), L.ptr(self.h0_global),
                                        L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                       self.math, s), "tsd_schnet_encoder")
+                                       L.ptr(self.filt_pool), self.filt_pool_count, self.math, s), "tsd_schnet_encoder")
         L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
                                  L.ptr(self.edge_inv_global), self.math, s), "tsd_pair_mlp")
         main.wait_stream(self.side)
