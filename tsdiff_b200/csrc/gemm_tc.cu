@@ -25,11 +25,14 @@
 namespace {
 using namespace tc;
 
-// dense-A kernels: 2 stages (~97 KB at N = 256) so TWO CTAs share an SM (2 x 256 TMEM columns) and every
-// tile of a batch-100 step is resident in a single wave; computed-A kernels: 4 stages, one CTA per SM
-__host__ __device__ constexpr int tc_stages(int akind) { return akind == TSD_A_PLAIN ? 2 : 4; }
-constexpr int TC_GROUP_THREADS = 64;                 // two warps per A-producer group
-constexpr int TC_GROUPS = 3;                         // warps 2-3, 4-5, 6-7
+// 2 stages (~97 KB at N = 256) so TWO CTAs share an SM (2 x 256 TMEM columns) and every tile of a
+// batch-100 step is resident in a single wave
+__host__ __device__ constexpr int tc_stages(int) { return 2; }
+// A-producer groups of the computed-operand kernels.  A group strides TC_GROUPS panels, and the
+// parity wait on a stage's `empty` barrier is only unambiguous when the group cannot fall two
+// phases behind, i.e. when TC_GROUPS <= number of stages: 2 stages -> 2 groups of three warps.
+constexpr int TC_GROUP_THREADS = 96;                 // warps 2-4 and 5-7
+constexpr int TC_GROUPS = 2;
 
 // A-operand prologue with the fast activations of this arithmetic mode.  A producer thread
 // always serves the same 16 rows (and the same 16-byte column chunk), so the per-row metadata
@@ -87,7 +90,7 @@ __device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, in
 }
 
 template <int ACT, int EPI, int AKIND>
-__global__ void __launch_bounds__(TC_THREADS, AKIND == TSD_A_PLAIN ? 2 : 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
     k_gemm_tf32(const GemmArgs p, int tmem_cols, const __grid_constant__ CUtensorMap map_a,
                 const __grid_constant__ CUtensorMap map_w) {
   extern __shared__ uint8_t smem_dyn[];
@@ -168,17 +171,18 @@ __global__ void __launch_bounds__(TC_THREADS, AKIND == TSD_A_PLAIN ? 2 : 1)
     }
   } else if (warp >= 2 && !dense_a) {
     // ------------------------------------------------------------ A producers (computed operand)
-    // three groups of two warps take panels round-robin: the global-load / SFU latency of one
-    // panel (which the proxy fence of its own threads cannot overlap) hides behind the other
-    // groups' panels, and 192 threads share the prologue arithmetic
-    const int group = (warp - 2) >> 1;
+    // the groups take panels round-robin: the global-load / SFU latency of one panel (which the
+    // proxy fence of its own threads cannot overlap) hides behind the other group's panel and the
+    // co-resident CTA
+    const int group = (warp - 2) / (TC_GROUP_THREADS / 32);
     const int t = tid - 64 - group * TC_GROUP_THREADS;
-    constexpr int ITEMS = (TC_BM * 8) / TC_GROUP_THREADS;  // 16 float4 per thread per panel
-    const int chunk = t & 7, row0 = t >> 3;                // item i -> row row0 + 8 i, 16-byte chunk `chunk`
+    constexpr int ROW_STEP = TC_GROUP_THREADS / 8;                              // rows between a thread's items
+    constexpr int ITEMS = (TC_BM * 8 + TC_GROUP_THREADS - 1) / TC_GROUP_THREADS;  // float4 per thread per panel
+    const int chunk = t & 7, row0 = t >> 3;  // item i -> row row0 + ROW_STEP i, 16-byte chunk `chunk`
     int meta0[ITEMS], meta1[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)  // rows past M are clamped: they only feed output rows that are never stored
-      tc_row_meta<AKIND>(p, min(m0 + row0 + 8 * i, M - 1), meta0[i], meta1[i]);
+      tc_row_meta<AKIND>(p, min(m0 + min(row0 + ROW_STEP * i, TC_BM - 1), M - 1), meta0[i], meta1[i]);
     for (int kb = group; kb < num_kb; kb += TC_GROUPS) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));
@@ -186,11 +190,13 @@ __global__ void __launch_bounds__(TC_THREADS, AKIND == TSD_A_PLAIN ? 2 : 1)
       const int k = kb * TC_BK + (chunk << 2);
       float4 v[ITEMS];
 #pragma unroll
-      for (int i = 0; i < ITEMS; ++i)  // branch-free on purpose: a per-item `m < M` branch serialises the 16 loads
-        v[i] = tf32_rn4(tc_load_a4<AKIND>(p, min(m0 + row0 + 8 * i, M - 1), k, meta0[i], meta1[i]));
+      for (int i = 0; i < ITEMS; ++i)  // branch-free on purpose: a per-item `m < M` branch serialises the loads
+        v[i] = tf32_rn4(
+            tc_load_a4<AKIND>(p, min(m0 + min(row0 + ROW_STEP * i, TC_BM - 1), M - 1), k, meta0[i], meta1[i]));
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i)
-        *reinterpret_cast<float4*>(a_panel + sw128_off(row0 + 8 * i, chunk)) = v[i];
+        if ((TC_BM * 8) % TC_GROUP_THREADS == 0 || i < ITEMS - 1 || row0 + ROW_STEP * i < TC_BM)
+          *reinterpret_cast<float4*>(a_panel + sw128_off(row0 + ROW_STEP * i, chunk)) = v[i];
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
       mbar_arrive(&bar_full[s]);
     }
