@@ -31,3 +31,16 @@ tot = sum(a[1] for a in agg.values())
 print("E =", eng.plan.edge_count(), " per-step kernel time %.1f us over %d kernels" % (tot / n, sum(a[0] for a in agg.values()) / n))
 for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
     print("%6.1f/step x%5.1f  avg %7.2f us  %5.1f%%  %s" % (a[1] / n, a[0] / n, a[1] / a[0], 100 * a[1] / tot, k))
+
+# timeline of the last replayed step: start offset, duration, stream of every kernel
+evs = [ev for ev in prof.events() if ev.device_type.name == 'CUDA']
+evs.sort(key=lambda e: e.time_range.start)
+per = len(evs) // n
+last = evs[-per:]
+t0 = last[0].time_range.start
+print("\ntimeline of one step (us from the first kernel's start):  start  dur  end  stream  kernel")
+for ev in last:
+    st = ev.time_range.start - t0
+    du = ev.time_range.end - ev.time_range.start
+    name = ev.name.replace('(anonymous namespace)::', '').replace('void ', '')
+    print("%8.1f %6.1f %8.1f  s%-3s %s" % (st, du, st + du, getattr(ev, 'device_resource_id', '?'), name[:60]))

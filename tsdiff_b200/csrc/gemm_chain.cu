@@ -206,10 +206,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_tf32(const ChainArgs p,
 
   if (threadIdx.x == 0) TC_STAMP(0);
   ChainCtx c;
+  c.tid = threadIdx.x, c.warp = c.tid >> 5, c.lane = c.tid & 31;
+  // predecessor-independent setup first (see launch_pdl): barriers and descriptor prefetch
+  if (c.tid == 0) {
+    for (int s = 0; s < CH_RING; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < 3; ++s) mbar_init(&bar_accum[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[0])) : "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
   c.M = p.M_ptr ? min(*p.M_ptr, p.M_cap) : p.M_cap;
   c.m0 = blockIdx.x * TC_BM;
   if (c.m0 >= c.M) return;
-  c.tid = threadIdx.x, c.warp = c.tid >> 5, c.lane = c.tid & 31;
   const int H = p.H;
   c.num_kb = H / TC_BK;
   c.w_panel_bytes = (uint32_t)H * TC_BK * 4;
@@ -224,16 +237,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_tf32(const ChainArgs p,
   c.bar_full = bar_full, c.bar_empty = bar_empty, c.bar_accum = bar_accum, c.s_bias = s_bias;
   c.issued = 0;
 
-  if (c.tid == 0) {
-    for (int s = 0; s < CH_RING; ++s) {
-      mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
-    }
-    for (int s = 0; s < 3; ++s) mbar_init(&bar_accum[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[0])) : "memory");
-  }
   if (c.warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"((uint32_t)tmem_cols)
@@ -275,7 +278,8 @@ int chain_launch(const ChainArgs& cc, const ChainMaps& maps, int tmem_cols, size
     TSD_CUDA(cudaFuncSetAttribute(k_chain_tf32<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  k_chain_tf32<KIND><<<tsd_ceil_div(cc.M_cap, TC_BM), CH_THREADS, smem, stream>>>(cc, maps, tmem_cols);
+  TSD_CUDA(launch_pdl(k_chain_tf32<KIND>, dim3(tsd_ceil_div(cc.M_cap, TC_BM)), dim3(CH_THREADS), smem, stream, cc, maps,
+                      tmem_cols));
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }
@@ -314,9 +318,10 @@ int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream) {
   cc.dbg = dbg;
   if (dbg) cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), stream);
   int rc = TSD_ERR_UNSUPPORTED;
-  if (chain_matches(c, CH_FILTER)) rc = chain_launch<CH_FILTER>(cc, maps, tmem_cols, smem, stream);
-  else if (chain_matches(c, CH_NODE3)) rc = chain_launch<CH_NODE3>(cc, maps, tmem_cols, smem, stream);
-  else if (chain_matches(c, CH_NODE2)) rc = chain_launch<CH_NODE2>(cc, maps, tmem_cols, smem, stream);
+  const int kind = chain_matches(c, CH_FILTER) ? CH_FILTER : chain_matches(c, CH_NODE3) ? CH_NODE3 : chain_matches(c, CH_NODE2) ? CH_NODE2 : -1;
+  if (kind == CH_FILTER) rc = chain_launch<CH_FILTER>(cc, maps, tmem_cols, smem, stream);
+  else if (kind == CH_NODE3) rc = chain_launch<CH_NODE3>(cc, maps, tmem_cols, smem, stream);
+  else if (kind == CH_NODE2) rc = chain_launch<CH_NODE2>(cc, maps, tmem_cols, smem, stream);
   if (rc != TSD_OK) return rc;
   if (dbg) {
     unsigned long long hb[64];

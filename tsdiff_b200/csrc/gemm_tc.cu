@@ -101,19 +101,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_dot[TC_BM];
 
-  if (threadIdx.x == 0) TC_STAMP(0);
-  const int M = p.M_ptr ? min(*p.M_ptr, p.M_cap) : p.M_cap;
-  const int m0 = blockIdx.x * TC_BM;
-  if (m0 >= M) return;  // uniform across the CTA, before any allocation
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, K = p.K;
-  if (tid == 0) TC_STAMP(1);
+  if (tid == 0) TC_STAMP(0);
   constexpr bool dense_a = AKIND == TSD_A_PLAIN;
-  const uint32_t b_panel_bytes = (uint32_t)N * TC_BK * 4;
-  const uint32_t stage_bytes = TC_A_PANEL_BYTES + b_panel_bytes;
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
-  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-
+  // predecessor-independent setup first (see launch_pdl): barriers and descriptor prefetch
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&bar_full[s], dense_a ? 1u : 1u + TC_GROUP_THREADS);
@@ -124,6 +115,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     if (dense_a) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
   }
+  pdl_wait();
+  pdl_trigger();
+  const int M = p.M_ptr ? min(*p.M_ptr, p.M_cap) : p.M_cap;
+  const int m0 = blockIdx.x * TC_BM;
+  if (m0 >= M) return;  // uniform across the CTA, before any allocation
+  const int N = p.N, K = p.K;
+  if (tid == 0) TC_STAMP(1);
+  const uint32_t b_panel_bytes = (uint32_t)N * TC_BK * 4;
+  const uint32_t stage_bytes = TC_A_PANEL_BYTES + b_panel_bytes;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"((uint32_t)tmem_cols)
@@ -318,7 +321,8 @@ int tc_launch(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorMap&
   if (g.dbg) {
     cudaMemsetAsync(g.dbg, 0, 64 * sizeof(unsigned long long), stream);
   }
-  k_gemm_tf32<ACT, EPI, AKIND><<<tsd_ceil_div(g.M_cap, TC_BM), TC_THREADS, smem, stream>>>(g, tmem_cols, map_a, map_w);
+  TSD_CUDA(launch_pdl(k_gemm_tf32<ACT, EPI, AKIND>, dim3(tsd_ceil_div(g.M_cap, TC_BM)), dim3(TC_THREADS), smem, stream, g,
+                      tmem_cols, map_a, map_w));
   TSD_LAUNCH_CHECK();
   if (g.dbg) {
     unsigned long long hb[64];

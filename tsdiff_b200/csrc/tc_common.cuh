@@ -2,6 +2,7 @@
 // TMA, UMMA descriptors, TMEM loads, the SWIZZLE_128B panel layout, fast activations, TF32
 // rounding and tensor-map encoding.  Everything is `static`/inline: no relocatable device code.
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 
 #include "gemm.cuh"
@@ -173,5 +174,41 @@ static inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+
+// ---- programmatic dependent launch ---------------------------------------------------------
+// A kernel launched with launch_pdl() may start while its stream predecessor is still running:
+// its CTAs become resident as SM resources free up, set up barriers / prefetch descriptors, and
+// block in pdl_wait() until the predecessor grid has completed and its writes are visible.
+// Rules kept by every kernel that uses it: pdl_wait() comes before the FIRST global-memory
+// access of every thread (also of CTAs that exit early), pdl_trigger() right after it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TSD_PDL");
+    const char* d = getenv("TSD_GEMM_DBG");  // the timeline mode memsets / syncs around every launch
+    on = (e && e[0] == '1' && !(d && d[0] == '1')) ? 1 : 0;  // opt-in: measured neutral on the LD step
+  }
+  return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace tc
