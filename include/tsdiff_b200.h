@@ -156,6 +156,12 @@ typedef struct {
   tsd_linear_t nn0, nn2, lin1, lin2, lin;
   float cutoff;
   int32_t smooth;
+  /* optional (tf32 encoder only, NULL otherwise): the NEXT block's lin1 folded into this block's
+   * lin -- fused_w (H,H) = lin1_next.W @ lin.W, fused_b (H) = lin1_next.W @ lin.b -- so that
+   * x1_next = lin1_next(h + lin(y)) = lin1_next(h) + fused_w y + fused_b needs one GEMM, not two,
+   * after the aggregation (see tsd_schnet_encoder). */
+  const float* fused_w;
+  const float* fused_b;
 } tsd_interaction_t;
 
 int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
@@ -173,12 +179,15 @@ int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* edges, const
  * blocks run as chained tensor-core kernels (filter network fused on the edges; lin2 -> lin ->
  * next block's lin1 fused on the nodes) and the edge kernels of different blocks overlap with each
  * other and with the node side on library-owned side streams (graph branches under capture).
- * filt_pool (optional): filt_pool_count x (E_cap, H) buffers so every block owns its filter buffer.
- * h_in is not modified; h_out may not alias h_in. */
+ * nf_pool (optional): nf_pool_count x (N, H) extra node buffers.  With >= 2 of them and
+ * fused_w / fused_b set on every block but the last, the node update is split: the critical
+ * kernel of a block computes only x1_next = lin1_next(h) + fused_w ssp(lin2(agg)) + fused_b (two
+ * chained GEMMs), while h' = h + lin(ssp(lin2(agg))) and lin1 of the block after next run beside
+ * the next aggregation.  h_in is not modified; h_out may not alias h_in. */
 int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                        const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
-                       float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* filt_pool,
-                       int32_t filt_pool_count, int32_t math, tsd_stream_t stream);
+                       float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* nf_pool,
+                       int32_t nf_pool_count, int32_t math, tsd_stream_t stream);
 
 /* The two building blocks of K4, exposed on their own for unit tests and for the per-kernel
  * roofline timing in bench.py:

@@ -40,7 +40,7 @@ class EdgeEncoder(C.Structure):
 
 class Interaction(C.Structure):
     _fields_ = [("nn0", Linear), ("nn2", Linear), ("lin1", Linear), ("lin2", Linear), ("lin", Linear),
-                ("cutoff", C.c_float), ("smooth", C.c_int32)]
+                ("cutoff", C.c_float), ("smooth", C.c_int32), ("fused_w", C.c_void_p), ("fused_b", C.c_void_p)]
 
 
 class Gine(C.Structure):

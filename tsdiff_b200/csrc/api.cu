@@ -260,11 +260,10 @@ extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t*
 // library-owned side stream + events for the fork/join inside tsd_schnet_encoder
 struct EncoderFork {
   static const int MAX_BLOCKS = 32;
-  cudaStream_t side = nullptr, edge2 = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
-  cudaEvent_t edge_done[MAX_BLOCKS], agg_done[MAX_BLOCKS];
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, xh_init = nullptr;
+  cudaEvent_t edge_done[MAX_BLOCKS], agg_done[MAX_BLOCKS], n2_done[MAX_BLOCKS];
   bool ready = false;
-  bool two_edge_streams = false;
   int init(int num_blocks) {
     if (num_blocks > MAX_BLOCKS) return TSD_ERR_UNSUPPORTED;
     if (ready) return TSD_OK;
@@ -273,16 +272,16 @@ struct EncoderFork {
     int prio_lo = 0, prio_hi = 0;
     TSD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     TSD_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
-    TSD_CUDA(cudaStreamCreateWithFlags(&edge2, cudaStreamNonBlocking));
+    TSD_CUDA(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, prio_hi));
     TSD_CUDA(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
     TSD_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     TSD_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    TSD_CUDA(cudaEventCreateWithFlags(&xh_init, cudaEventDisableTiming));
     for (int i = 0; i < MAX_BLOCKS; ++i) {
       TSD_CUDA(cudaEventCreateWithFlags(&edge_done[i], cudaEventDisableTiming));
       TSD_CUDA(cudaEventCreateWithFlags(&agg_done[i], cudaEventDisableTiming));
+      TSD_CUDA(cudaEventCreateWithFlags(&n2_done[i], cudaEventDisableTiming));
     }
-    const char* e = getenv("TSD_ENCODER_EDGE_STREAMS");
-    two_edge_streams = e && atoi(e) == 2;
     ready = true;
     return TSD_OK;
   }
@@ -339,12 +338,11 @@ extern "C" int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* e
 
 // Whole SchNet encoder (schnet.py:203-225).  fp32 mode: one tsd_cfconv_layer per block.  tf32
 // mode: per block ONE chained filter-network kernel on the edges, the segmented aggregation, and
-// ONE chained node kernel that also produces the next block's x1 = lin1(h') -- 3 launches per
-// block instead of 6 and no (E,H) / (N,H) intermediate round trips.
+// chained node kernels -- no (E,H) / (N,H) intermediate round trips.
 extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                                   const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
-                                  float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* filt_pool,
-                                  int32_t filt_pool_count, int32_t math, tsd_stream_t stream) {
+                                  float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* nf_pool,
+                                  int32_t nf_pool_count, int32_t math, tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && edge_attr && blocks && num_blocks >= 1 && h_in && h_out && ef0 && ef1 && nf0 && nf1 && nf2);
   cudaStream_t s = tsd_cu(stream);
   const int H = blocks[0].lin.out_features;
@@ -364,41 +362,54 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     }
     return TSD_OK;
   }
-  // The filter networks depend only on edge_attr, not on h: block l+1's edge kernel can run while
-  // block l's aggregation / node update is in flight.  Fork a side stream for the node-side chain
-  // (x1_0, agg_l, node kernel_l); the main stream runs the edge kernels back to back, alternating
-  // between two filter buffers.  The edge kernel's second wave leaves most SMs idle (188-263 tiles
-  // on 148 SMs), which is where the 15-CTA node kernels and the aggregation execute.  Inside a
-  // CUDA-graph capture the event waits become graph edges.
+  // Dependency structure of a block l:   filter_l (edges; depends on edge_attr only)
+  //                                      agg_l    (needs filter_l and x1_l)
+  //                                      node_l   (needs agg_l; produces h_{l+1} and x1_{l+1})
+  // The serial chain is agg_l -> node_l -> agg_{l+1}: 7 x (aggregate + 3 chained GEMMs).  Streams:
+  //   caller's stream : the filter kernels back to back, alternating between two filter buffers
+  //                     (their second wave leaves most SMs idle, which is where the node side runs)
+  //   side            : x1_0, then per block agg_l and the CRITICAL node kernel
+  //   side2           : the node work that is NOT needed by the next aggregation (split mode)
+  // Split mode (fused weights + two extra node buffers): the next aggregation only needs
+  //   x1_{l+1} = lin1_{l+1}(h_l + lin_l(y)) = xh_l + fused_w y + fused_b,  y = ssp(lin2_l(agg_l)),
+  // where xh_l = lin1_{l+1}(h_l) is known one block EARLIER.  So the critical kernel is two chained
+  // GEMMs (lin2, fused), and a second kernel on side2 computes h_{l+1} = h_l + lin_l(y) and
+  // xh_{l+1} = lin1_{l+2}(h_{l+1}) beside agg_{l+1}.  Inside a CUDA-graph capture the event waits
+  // become graph edges.
   static EncoderFork fk;
   TSD_TRY(fk.init(num_blocks));
-  cudaStream_t side = fk.side, edge2 = fk.edge2;
+  cudaStream_t side = fk.side, side2 = fk.side2;
+  bool split = nf_pool && nf_pool_count >= 2 && num_blocks >= 2;
+  for (int l = 0; l + 1 < num_blocks && split; ++l) split = blocks[l].fused_w && blocks[l].fused_b;
+  {
+    const char* e = getenv("TSD_ENCODER_SPLIT");
+    if (e && e[0] == '0') split = false;
+  }
+  const size_t node_elems = (size_t)batch->num_nodes * H;
+  float* aggbuf[2] = {nf1, split ? nf2 : nf1};
+  float* xh[2] = {nf_pool, split ? nf_pool + node_elems : nullptr};
   TSD_CUDA(cudaEventRecord(fk.fork, s));
   TSD_CUDA(cudaStreamWaitEvent(side, fk.fork, 0));
-  TSD_CUDA(cudaStreamWaitEvent(edge2, fk.fork, 0));
+  TSD_CUDA(cudaStreamWaitEvent(side2, fk.fork, 0));
   GemmArgs g = node_gemm(batch, blocks[0].lin1);  // x1 of block 0
   g.A = h_in;
   g.C = nf0;
   TSD_TRY(tsd_gemm(g, math, side));
+  if (split) {
+    g = node_gemm(batch, blocks[1].lin1);  // xh_0 = lin1_1(h_0)
+    g.A = h_in;
+    g.C = xh[0];
+    TSD_TRY(tsd_gemm(g, math, side2));
+    TSD_CUDA(cudaEventRecord(fk.xh_init, side2));
+  }
   const float* h = h_in;
-  // filter buffers: a caller-provided pool (one per block: no reuse waits) or the two scratch buffers
-  const int nbuf = (filt_pool && filt_pool_count >= 2) ? (filt_pool_count < num_blocks ? filt_pool_count : num_blocks) : 2;
-  const size_t buf_elems = (size_t)(batch->edge_capacity > 0 ? batch->edge_capacity : 1) * H;
-  auto filt_of = [&](int l) -> float* {
-    if (filt_pool && filt_pool_count >= 2) return filt_pool + (size_t)(l % nbuf) * buf_elems;
-    return (l & 1) ? ef0 : ef1;
-  };
-  // The edge kernels of consecutive blocks are independent of each other too: they alternate
-  // between two streams so block l+1's tiles fill the SMs that block l's second wave leaves idle.
   for (int l = 0; l < num_blocks; ++l) {
     const tsd_interaction_t& b = blocks[l];
-    float* filt = filt_of(l);
-    // NOTE measured: letting consecutive blocks' edge kernels run concurrently (alternating streams,
-    // one filter buffer per block) was SLOWER (33-36 vs 38.7 samples/s): the queued edge tiles
-    // starve the serial node-side chain even with a high-priority stream.  Edge kernels therefore
-    // stay on the caller's stream; TSD_ENCODER_EDGE_STREAMS=2 re-enables the experiment.
-    cudaStream_t es = (fk.two_edge_streams && (l & 1)) ? edge2 : s;
-    if (l >= nbuf) TSD_CUDA(cudaStreamWaitEvent(es, fk.agg_done[l - nbuf], 0));  // buffer reuse: agg_{l-nbuf} has read it
+    float* filt = (l & 1) ? ef0 : ef1;
+    // (measured: letting consecutive blocks' filter kernels run concurrently on two streams with one
+    // buffer per block was SLOWER, 33-36 vs 38.7 samples/s: the queued edge tiles starve the serial
+    // node-side chain even with a high-priority stream.)
+    if (l >= 2) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - 2], 0));  // buffer reuse: agg_{l-2} has read it
     ChainArgs c;
     memset(&c, 0, sizeof(c));
     c.M_cap = batch->edge_capacity;
@@ -412,34 +423,71 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     c.st[1].cutoff = b.cutoff;
     c.st[1].smooth = b.smooth;
     c.st[1].store = filt;
-    TSD_TRY(tsd_chain_tf32(c, es));
-    TSD_CUDA(cudaEventRecord(fk.edge_done[l], es));
+    TSD_TRY(tsd_chain_tf32(c, s));
+    TSD_CUDA(cudaEventRecord(fk.edge_done[l], s));
     // node side of block l (issued in the same loop iteration so that, under stream capture, every
     // event is recorded in the capture before anything waits on it)
+    float* agg = aggbuf[l & 1];
     TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
-    TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, nf0, filt, nf1,
+    TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, nf0, filt, agg,
                                         side));
     TSD_CUDA(cudaEventRecord(fk.agg_done[l], side));
-    // node update: h' = h + lin(ssp(lin2(agg))) and, unless this is the last block, x1' = lin1_next(h')
     memset(&c, 0, sizeof(c));
     c.M_cap = batch->num_nodes;
     c.H = H;
-    c.A = nf1;
+    c.A = agg;
     c.st[0] = chain_stage(b.lin2, TSD_ACT_SSP);
-    c.st[1] = chain_stage(b.lin, TSD_ACT_NONE);
-    c.st[1].residual = h;
-    c.st[1].store = h_out;
-    if (l + 1 < num_blocks) {
-      c.num_stages = 3;
-      c.st[2] = chain_stage(blocks[l + 1].lin1, TSD_ACT_NONE);
-      c.st[2].store = nf0;
-    } else {
+    if (!split) {
+      // node update: h' = h + lin(ssp(lin2(agg))) and, unless this is the last block, x1' = lin1_next(h')
+      c.st[1] = chain_stage(b.lin, TSD_ACT_NONE);
+      c.st[1].residual = h;
+      c.st[1].store = h_out;
+      if (l + 1 < num_blocks) {
+        c.num_stages = 3;
+        c.st[2] = chain_stage(blocks[l + 1].lin1, TSD_ACT_NONE);
+        c.st[2].store = nf0;
+      } else {
+        c.num_stages = 2;
+      }
+      TSD_TRY(tsd_chain_tf32(c, side));
+    } else if (l + 1 < num_blocks) {
+      // side2: h_{l+1} = h_l + lin(y) and xh_{l+1} = lin1_{l+2}(h_{l+1}); needs agg_l and (stream order) h_l
+      ChainArgs c2 = c;
+      c2.st[1] = chain_stage(b.lin, TSD_ACT_NONE);
+      c2.st[1].residual = h;
+      c2.st[1].store = h_out;
+      if (l + 2 < num_blocks) {
+        c2.num_stages = 3;
+        c2.st[2] = chain_stage(blocks[l + 2].lin1, TSD_ACT_NONE);
+        c2.st[2].store = xh[(l + 1) & 1];
+      } else {
+        c2.num_stages = 2;
+      }
+      TSD_CUDA(cudaStreamWaitEvent(side2, fk.agg_done[l], 0));
+      TSD_TRY(tsd_chain_tf32(c2, side2));
+      TSD_CUDA(cudaEventRecord(fk.n2_done[l], side2));
+      // side (critical): x1_{l+1} = xh_l + fused_w y + fused_b
+      tsd_linear_t fused = b.lin;
+      fused.weight = b.fused_w;
+      fused.bias = b.fused_b;
       c.num_stages = 2;
+      c.st[1] = chain_stage(fused, TSD_ACT_NONE);
+      c.st[1].residual = xh[l & 1];
+      c.st[1].store = nf0;
+      TSD_CUDA(cudaStreamWaitEvent(side, l == 0 ? fk.xh_init : fk.n2_done[l - 1], 0));
+      TSD_TRY(tsd_chain_tf32(c, side));
+    } else {
+      // last block: only h_out is needed; h_{L-1} comes from side2
+      c.num_stages = 2;
+      c.st[1] = chain_stage(b.lin, TSD_ACT_NONE);
+      c.st[1].residual = h;
+      c.st[1].store = h_out;
+      TSD_CUDA(cudaStreamWaitEvent(side, fk.n2_done[l - 1], 0));
+      TSD_TRY(tsd_chain_tf32(c, side));
     }
-    TSD_TRY(tsd_chain_tf32(c, side));
     h = h_out;
   }
-  TSD_CUDA(cudaEventRecord(fk.join2, edge2));
+  TSD_CUDA(cudaEventRecord(fk.join2, side2));
   TSD_CUDA(cudaStreamWaitEvent(s, fk.join2, 0));
   TSD_CUDA(cudaEventRecord(fk.join, side));
   TSD_CUDA(cudaStreamWaitEvent(s, fk.join, 0));

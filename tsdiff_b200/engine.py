@@ -136,16 +136,11 @@ class _WeightView:
         return shadow
 
 
-def _filter_pool(plan, hidden, num_blocks, math):
-    """tf32 mode: one (E_cap, H) filter buffer per interaction block, so the blocks' edge kernels
-    can all be in flight without waiting for a buffer (capped at 4 GiB; fewer buffers just add
-    reuse dependencies)."""
-    import os
-    if math != "tf32" or os.environ.get("TSD_ENCODER_EDGE_STREAMS") != "2":
-        return None, 0  # default: two alternating scratch buffers (see tsd_schnet_encoder)
-    per = max(plan.edge_capacity, 1) * hidden * 4
-    count = max(2, min(num_blocks, (4 << 30) // per))
-    return torch.empty(count * max(plan.edge_capacity, 1) * hidden, dtype=torch.float32, device=plan.device), count
+def _node_pool(plan, hidden, math):
+    """tf32 mode: the two extra (N, H) buffers of the encoder's split node update (tsd_schnet_encoder)."""
+    if math != "tf32":
+        return None, 0
+    return torch.empty(2 * max(plan.num_nodes, 1) * hidden, dtype=torch.float32, device=plan.device), 2
 
 
 def _edge_encoder_struct(enc, act, cat=None, cat_act="none", wv=lambda w: w):
@@ -166,7 +161,7 @@ def _edge_encoder_struct(enc, act, cat=None, cat_act="none", wv=lambda w: w):
     return s, keep
 
 
-def _interaction_struct(blk, wv=lambda w: w):
+def _interaction_struct(blk, wv=lambda w: w, next_blk=None):
     s = L.Interaction()
     s.nn0 = L.linear(wv(blk.conv.nn[0].weight), blk.conv.nn[0].bias)
     s.nn2 = L.linear(wv(blk.conv.nn[2].weight), blk.conv.nn[2].bias)
@@ -175,7 +170,22 @@ def _interaction_struct(blk, wv=lambda w: w):
     s.lin = L.linear(wv(blk.lin.weight), blk.lin.bias)
     s.cutoff = float(blk.conv.cutoff)
     s.smooth = int(bool(blk.conv.smooth))
+    if next_blk is not None and getattr(wv, "tf32", False):
+        # the next block's lin1 folded into this block's lin (schnet.py:101 after :128):
+        # lin1_next(h + lin(y)) = lin1_next(h) + (W1 W_lin) y + W1 b_lin
+        with torch.no_grad():
+            w1 = next_blk.conv.lin1.weight.double()
+            fw = (w1 @ blk.lin.weight.double()).float().contiguous()
+            fb = (w1 @ blk.lin.bias.double()).float().contiguous()
+        wv.keep.append(fb)
+        s.fused_w = wv(fw).data_ptr()
+        s.fused_b = fb.data_ptr()
     return s
+
+
+def _interaction_structs(blocks, wv):
+    blocks = list(blocks)
+    return [_interaction_struct(b, wv, blocks[i + 1] if i + 1 < len(blocks) else None) for i, b in enumerate(blocks)]
 
 
 def _interaction_array(blocks):
@@ -226,7 +236,7 @@ class CondensedScoreEngine:
         # d_emb, tmp, ea1, ea2, ef0, ef1, tmp2
         self.ws = _Scratch(plan, h, 7, 4)
         self.side = torch.cuda.Stream(device=plan.device)  # second-graph edge embedding runs beside the encoder
-        self.filt_pool, self.filt_pool_count = _filter_pool(plan, h, len(self.models[0].encoder.interactions), math)
+        self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
         self.edge_inv = torch.zeros(max(plan.edge_capacity, 1), dtype=torch.float32, device=plan.device)
         atom_type = atom_type.to(torch.long).contiguous()
         r_feat = r_feat.to(torch.long).contiguous()
@@ -241,7 +251,7 @@ class CondensedScoreEngine:
                                                  h // 2, L.ptr(z), _stream()), "tsd_condensed_node_embed")
             enc, keep = _edge_encoder_struct(m.edge_encoder, m.edge_encoder.mlp.act, m.edge_cat,
                                              L_act(cfg.edge_cat_act), self.wv)
-            blocks = _interaction_array([_interaction_struct(b, self.wv) for b in m.encoder.interactions])
+            blocks = _interaction_array(_interaction_structs(m.encoder.interactions, self.wv))
             pair = _pair_mlp_struct(m.grad_dist_mlp, self.wv)
             self.members.append({"z": z, "enc": enc, "keep": keep, "blocks": blocks, "pair": pair})
 
@@ -271,7 +281,7 @@ class CondensedScoreEngine:
                 ea_out = ea1
             L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
                                            L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                           L.ptr(self.filt_pool), self.filt_pool_count, self.math, s),
+                                           L.ptr(self.nf_pool), self.nf_pool_count, self.math, s),
                     "tsd_schnet_encoder")
             if self.two_graphs:
                 main.wait_stream(self.side)
@@ -312,7 +322,7 @@ class DualScoreEngine:
         self.cutoff = float(cfg.cutoff)
         self.ws = _Scratch(plan, h, 7, 7)
         self.side = torch.cuda.Stream(device=plan.device)  # the local (GIN) branch runs beside the global one
-        self.filt_pool, self.filt_pool_count = _filter_pool(plan, h, len(model.encoder_global.interactions), math)
+        self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
         cap = max(plan.edge_capacity, 1)
         # TS variant (edge_cat): the local edge encoder needs its own d_emb / tmp scratch
         self.local_scratch = ([torch.empty(cap, h, dtype=torch.float32, device=plan.device) for _ in range(2)]
@@ -327,7 +337,7 @@ class DualScoreEngine:
                                                     model.edge_cat_global if self.ts else None, cat_act, self.wv)
         self.enc_l, self._k2 = _edge_encoder_struct(model.edge_encoder_local, act,
                                                     model.edge_cat_local if self.ts else None, cat_act, self.wv)
-        self.blocks = _interaction_array([_interaction_struct(b, self.wv) for b in model.encoder_global.interactions])
+        self.blocks = _interaction_array(_interaction_structs(model.encoder_global.interactions, self.wv))
         n_local = len(model.encoder_local.convs)
         self.gines = [_gine_struct(c, i < n_local - 1, self.wv) for i, c in enumerate(model.encoder_local.convs)]
         self.pair_g = _pair_mlp_struct(model.grad_global_dist_mlp, self.wv)
@@ -377,7 +387,7 @@ class DualScoreEngine:
                                    self.math, s), "tsd_edge_embed")
         L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea_g), self.blocks, len(self.blocks), L.ptr(self.h0_global),
                                        L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                       L.ptr(self.filt_pool), self.filt_pool_count, self.math, s), "tsd_schnet_encoder")
+                                       L.ptr(self.nf_pool), self.nf_pool_count, self.math, s), "tsd_schnet_encoder")
         L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
                                  L.ptr(self.edge_inv_global), self.math, s), "tsd_pair_mlp")
         main.wait_stream(self.side)
