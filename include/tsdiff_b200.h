@@ -87,6 +87,15 @@ int tsd_version(void);
 /* number of kernel launches this library has issued (host counter; bench.py's gpu_launches) */
 int64_t tsd_launch_count(void);
 
+/* Scratch a caller has to provide for one eps-net evaluation (the library never allocates caller
+ * memory).  network: 0 = condensenc (path B), 1 = dualenc (path A).
+ * Outputs (any may be NULL): bytes of ONE (E_cap, hidden) edge buffer and of ONE (N, hidden)
+ * node buffer, and how many of each the kernel sequence of the network uses, including the two
+ * pooled node buffers of the tf32 encoder (tsd_schnet_encoder's nf_pool). */
+int tsd_workspace_bytes(int32_t num_nodes, int32_t edge_capacity, int32_t hidden, int32_t network, int32_t math,
+                        uint64_t* edge_buffer_bytes, uint64_t* node_buffer_bytes, int32_t* edge_buffers,
+                        int32_t* node_buffers);
+
 /* ---- K1: bond-order (k-hop) pair tables; position independent, once per batch -------------
  * mode 0 (path B, replaces models/common.py:115-202 `_extend_ts_graph_order`): reactant
  *   (type / 22) and product (type % 22) bond graphs are extended separately; table value =

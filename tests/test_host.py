@@ -106,3 +106,16 @@ def test_shards_partition_the_batch():
         assert p["atom_offset"] == off
         off += p["atom_type"].numel()
         assert int(p["bond_index"].min()) >= 0 and int(p["bond_index"].max()) < p["atom_type"].numel()
+
+
+def test_workspace_bytes_is_host_arithmetic():
+    """tsd_workspace_bytes needs no GPU: buffer sizes and counts for both networks / arithmetic modes."""
+    import ctypes as C
+    lib = L.load()
+    eb, nb, ne, nn = C.c_uint64(), C.c_uint64(), C.c_int32(), C.c_int32()
+    for network, math, want_nodes in ((0, 0, 4), (0, 1, 6), (1, 0, 7), (1, 1, 9)):
+        rc = lib.tsd_workspace_bytes(1750, 28900, 256, network, math, C.byref(eb), C.byref(nb), C.byref(ne), C.byref(nn))
+        assert rc == 0
+        assert eb.value == 28900 * 256 * 4 and nb.value == 1750 * 256 * 4
+        assert ne.value == 7 and nn.value == want_nodes
+    assert lib.tsd_workspace_bytes(10, 10, 0, 0, 0, None, None, None, None) != 0  # invalid hidden

@@ -68,6 +68,7 @@ _P = C.c_void_p
 _SIGNATURES = {
     "tsd_version": [],
     "tsd_launch_count": [],
+    "tsd_workspace_bytes": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P],
     "tsd_linear": [C.c_int32, _P, _P, C.POINTER(Linear), C.c_int32, _P, C.c_int32, _P],
     "tsd_round_tf32": [_P, _P, C.c_int64, _P],
     "tsd_cfconv_aggregate": [C.POINTER(Batch), C.POINTER(Edges), C.c_int32, _P, _P, _P, _P],

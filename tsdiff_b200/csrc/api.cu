@@ -30,6 +30,20 @@ int tsd_record_cuda_error(cudaError_t e) {
 extern "C" int tsd_last_cuda_error(void) { return g_last_cuda_error; }
 extern "C" int tsd_version(void) { return 100; }
 
+extern "C" int tsd_workspace_bytes(int32_t num_nodes, int32_t edge_capacity, int32_t hidden, int32_t network,
+                                   int32_t math, uint64_t* edge_buffer_bytes, uint64_t* node_buffer_bytes,
+                                   int32_t* edge_buffers, int32_t* node_buffers) {
+  TSD_REQUIRE(num_nodes >= 0 && edge_capacity >= 0 && hidden > 0 && (network == 0 || network == 1));
+  const uint64_t e = (uint64_t)(edge_capacity > 0 ? edge_capacity : 1), n = (uint64_t)(num_nodes > 0 ? num_nodes : 1);
+  if (edge_buffer_bytes) *edge_buffer_bytes = e * (uint64_t)hidden * sizeof(float);
+  if (node_buffer_bytes) *node_buffer_bytes = n * (uint64_t)hidden * sizeof(float);
+  // edge: d_emb, tmp, edge_attr (graph a), edge_attr (graph b / local), two filter buffers, tmp of the second embedding
+  if (edge_buffers) *edge_buffers = 7;
+  // node: h, x1, agg, spare (+ h_local, x1_local, agg_local for the GIN branch of path A) + encoder pool (tf32)
+  if (node_buffers) *node_buffers = (network == 0 ? 4 : 7) + (math == TSD_MATH_TF32 ? 2 : 0);
+  return TSD_OK;
+}
+
 extern "C" const char* tsd_error_string(int code) {
   switch (code) {
     case TSD_OK: return "ok";

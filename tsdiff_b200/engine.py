@@ -110,8 +110,13 @@ class BatchPlan:
 class _Scratch:
     """Capacity-sized activation buffers shared by all ensemble members."""
 
-    def __init__(self, plan, hidden, n_edge_bufs, n_node_bufs):
+    def __init__(self, plan, hidden, n_edge_bufs, n_node_bufs, network=0, math="fp32"):
         dev = plan.device
+        # the library states what its kernel sequence needs (tsd_workspace_bytes); keep the two in step
+        ne, nn = C.c_int32(), C.c_int32()
+        L.check(L.load().tsd_workspace_bytes(plan.num_nodes, plan.edge_capacity, hidden, network, L.MATH[math], None, None,
+                                             C.byref(ne), C.byref(nn)), "tsd_workspace_bytes")
+        assert ne.value == n_edge_bufs and nn.value == n_node_bufs + (2 if math == "tf32" else 0), (ne.value, nn.value)
         cap = max(plan.edge_capacity, 1)
         self.edge = [torch.empty(cap, hidden, dtype=torch.float32, device=dev) for _ in range(n_edge_bufs)]
         self.node = [torch.empty(max(plan.num_nodes, 1), hidden, dtype=torch.float32, device=dev)
@@ -234,7 +239,7 @@ class CondensedScoreEngine:
         self.hidden = h
         self.cutoff = float(cfg.edge_cutoff)
         # d_emb, tmp, ea1, ea2, ef0, ef1, tmp2
-        self.ws = _Scratch(plan, h, 7, 4)
+        self.ws = _Scratch(plan, h, 7, 4, 0, math)
         self.side = torch.cuda.Stream(device=plan.device)  # second-graph edge embedding runs beside the encoder
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
         self.edge_inv = torch.zeros(max(plan.edge_capacity, 1), dtype=torch.float32, device=plan.device)
@@ -320,7 +325,7 @@ class DualScoreEngine:
         h = int(cfg.hidden_dim)
         self.hidden = h
         self.cutoff = float(cfg.cutoff)
-        self.ws = _Scratch(plan, h, 7, 7)
+        self.ws = _Scratch(plan, h, 7, 7, 1, math)
         self.side = torch.cuda.Stream(device=plan.device)  # the local (GIN) branch runs beside the global one
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
         cap = max(plan.edge_capacity, 1)
