@@ -346,6 +346,33 @@ def test_cfconv_aggregate_bit_exact_vs_sequential_scatter(syn4):
     assert torch.equal(agg.cpu(), ref)
 
 
+def test_cfconv_aggregate_staged_kernel_bit_exact_at_stress_size():
+    """BASELINE config 5 shape: 80 reactions of ~60 atoms, cutoff 15 A -> edge capacity > 2^18, where
+    tsd_cfconv_aggregate switches to the graph-staged kernel (x1 rows in shared memory, prefetched
+    in-CSR).  Same sums in the same order as a sequential scatter_add: bit-exact."""
+    lib = L.load()
+    g = make_batch(80, seed=33, min_atoms=55, max_atoms=65)
+    n = g["atom_type"].numel()
+    torch.manual_seed(10)
+    pos = torch.randn(n, 3) * 5.0
+    d = to_dev(g, DEV)
+    plan = E.BatchPlan(0, d["batch"], d["bond_index"], d["bond_type"], 4, 3)
+    assert plan.edge_capacity >= (1 << 18)
+    plan.build_edges(pos.to(DEV).contiguous(), 15.0)
+    e, idx = _plan_edges(plan)
+    h = 256
+    x1 = torch.randn(n, h)
+    filt = torch.randn(e, h)
+    filt_dev = torch.zeros(plan.edge_capacity, h, device=DEV)
+    filt_dev[:e] = filt.to(DEV)
+    agg = torch.empty(n, h, device=DEV)
+    L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_batch), C.byref(plan.c_edges), h, L.ptr(x1.to(DEV)),
+                                     L.ptr(filt_dev), L.ptr(agg),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "aggregate")
+    ref = tp.scatter_add(x1[idx[0]] * filt, idx[1], dim=0, dim_size=n)
+    assert torch.equal(agg.cpu(), ref)
+
+
 def test_stress_shape_forward_vs_oracle():
     """BASELINE config 5 shape at reduced count: ~60-atom reactions, cutoff enlarged to 15 A so the
     32-neighbour cap binds (asymmetric radius graph).  Full path-B forward vs the oracle."""

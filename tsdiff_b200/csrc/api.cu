@@ -12,6 +12,28 @@ int tsd_launch_cfconv_aggregate(int num_nodes, int H, const int* in_ptr, const i
 int tsd_launch_cfconv_aggregate_staged(const tsd_batch_t* b, int H, const int* in_ptr, const int* in_eid,
                                        const int* in_src, const float* x1, const float* filt, float* agg,
                                        cudaStream_t s);
+
+// CFConv aggregation, two kernels for two regimes (profiles/scripts/time_agg.py):
+//   node-parallel (warp per target node and 128-channel slab): most memory-level parallelism for
+//     a small edge list -- 20 us cold at batch 100 (E = 33.5k), where the graph-staged kernel
+//     needs 33 us (only G x H/128 CTAs);
+//   graph-staged (CTA per reaction and slab, the reaction's x1 rows in shared memory, in-CSR
+//     bounds and next-node ids prefetched): the x1 gather stays on the SM, so only the filter
+//     rows stream -- 4.64 TB/s = 72 % of the measured HBM copy bandwidth at BASELINE config 5
+//     (1000 reactions x ~60 atoms, E = 2.3M) against 3.9 TB/s for the node-parallel kernel.
+// The switch uses the host-side edge capacity (the valid count lives on the device).
+static int tsd_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int H, const float* x1, const float* filt,
+                         float* agg, cudaStream_t s) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* v = getenv("TSD_AGG_VARIANT");
+    forced = v ? atoi(v) : -1;
+  }
+  const bool staged = forced == 5 || (forced < 0 && batch->edge_capacity >= (1 << 18) && batch->max_graph_nodes <= 256);
+  if (staged) return tsd_launch_cfconv_aggregate_staged(batch, H, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt, agg, s);
+  return tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt, agg, s);
+}
+
 int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
                               const int* local_tab, const float* h, const float* ea, const float* eps, float* out,
                               cudaStream_t s);
@@ -170,7 +192,7 @@ extern "C" int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edg
   g.A = h_in;
   g.C = nf0;
   TSD_TRY(tsd_gemm(g, math, s));
-  TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, F, edges->in_ptr, edges->in_eid, edges->in_src, nf0, ef1, nf1, s));
+  TSD_TRY(tsd_aggregate(batch, edges, F, nf0, ef1, nf1, s));
   // h_out = h_in + lin(ssp(lin2(agg)))
   g = node_gemm(batch, blk->lin2);
   g.A = nf1;
@@ -260,15 +282,7 @@ extern "C" int tsd_linear(int32_t rows, const int32_t* rows_dev, const float* x,
 extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t channels,
                                     const float* x1, const float* filt, float* agg, tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && x1 && filt && agg);
-  // TSD_AGG_VARIANT=5 selects the graph-staged kernel (x1 rows in shared memory).  It was measured
-  // SLOWER than the node-parallel kernel at batch 100 (30 us vs 18 us warm at E = 33.5k: only
-  // G x H/128 CTAs, too little memory-level parallelism), so it is kept for experiments only.
-  const char* v = getenv("TSD_AGG_VARIANT");
-  if (v && atoi(v) == 5)
-    return tsd_launch_cfconv_aggregate_staged(batch, channels, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt, agg,
-                                              tsd_cu(stream));
-  return tsd_launch_cfconv_aggregate(batch->num_nodes, channels, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt,
-                                     agg, tsd_cu(stream));
+  return tsd_aggregate(batch, edges, channels, x1, filt, agg, tsd_cu(stream));
 }
 
 // library-owned side stream + events for the fork/join inside tsd_schnet_encoder
@@ -443,8 +457,7 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     // event is recorded in the capture before anything waits on it)
     float* agg = aggbuf[l & 1];
     TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
-    TSD_TRY(tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, nf0, filt, agg,
-                                        side));
+    TSD_TRY(tsd_aggregate(batch, edges, H, nf0, filt, agg, side));
     TSD_CUDA(cudaEventRecord(fk.agg_done[l], side));
     memset(&c, 0, sizeof(c));
     c.M_cap = batch->num_nodes;

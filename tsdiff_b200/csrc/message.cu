@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_cfconv_aggregate(int num_nodes, int H, 
   if (active) *reinterpret_cast<float4*>(agg + (size_t)node * H + off) = acc;
 }
 
-// Graph-staged variant (default): one CTA per (reaction, 128-channel slab).  The x1 rows of the
+// Graph-staged variant (large edge lists, see tsd_aggregate in api.cu): one CTA per (reaction, 128-channel slab).  The x1 rows of the
 // reaction (<= 256 x 512 B) are staged in shared memory once, so the per-edge gather of the
 // source features never leaves the SM; only the filter rows stream from L2/HBM, each exactly
 // once.  (The node-parallel kernel above re-reads a 512-byte x1 slab per edge from L2: E*H*4
@@ -88,15 +88,32 @@ __global__ void __launch_bounds__(256) k_cfconv_aggregate_staged(int H, const in
   for (int i = warp; i < n; i += nwarps)
     sx[i * 32 + lane] = active ? __ldg(reinterpret_cast<const float4*>(x1 + (size_t)(n0 + i) * H + off))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  // in-CSR bounds of all of this warp's nodes in one coalesced round trip (lane k <-> node warp + k nwarps),
+  // and the edge / source ids of the NEXT node prefetched while the current node's rows stream:
+  // the dependent chain per node is then just the row loads.
+  const int my_nodes = n > warp ? (n - warp + nwarps - 1) / nwarps : 0;  // <= 32 for n <= 256, 8 warps
+  int beg_l = 0, end_l = 0;
+  if (lane < my_nodes) {
+    beg_l = in_ptr[n0 + warp + lane * nwarps];
+    end_l = in_ptr[n0 + warp + lane * nwarps + 1];
+  }
   __syncthreads();
-  for (int i = warp; i < n; i += nwarps) {
-    const int node = n0 + i;
-    const int beg = in_ptr[node], end = in_ptr[node + 1];
+  int beg = __shfl_sync(TSD_FULL_MASK, beg_l, 0), end = __shfl_sync(TSD_FULL_MASK, end_l, 0);
+  int e_l = (my_nodes > 0 && lane < end - beg) ? in_eid[beg + lane] : 0;
+  int r_l = (my_nodes > 0 && lane < end - beg) ? in_src[beg + lane] - n0 : 0;
+  for (int k = 0; k < my_nodes; ++k) {
+    const int node = n0 + warp + k * nwarps;
+    const int nbeg = __shfl_sync(TSD_FULL_MASK, beg_l, min(k + 1, 31)), nend = __shfl_sync(TSD_FULL_MASK, end_l, min(k + 1, 31));
+    const bool has_next = k + 1 < my_nodes;
+    const int e_n = (has_next && lane < nend - nbeg) ? in_eid[nbeg + lane] : 0;   // prefetch (first 32 in-edges)
+    const int r_n = (has_next && lane < nend - nbeg) ? in_src[nbeg + lane] - n0 : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
-      const int e_l = lane < cnt ? in_eid[base + lane] : 0;
-      const int r_l = lane < cnt ? in_src[base + lane] - n0 : 0;
+      if (base != beg) {  // degree > 32: later batches are fetched on demand
+        e_l = lane < cnt ? in_eid[base + lane] : 0;
+        r_l = lane < cnt ? in_src[base + lane] - n0 : 0;
+      }
       int j = 0;
       for (; j + UNROLL <= cnt; j += UNROLL) {
         float4 w[UNROLL];
@@ -118,6 +135,7 @@ __global__ void __launch_bounds__(256) k_cfconv_aggregate_staged(int H, const in
       }
     }
     if (active) *reinterpret_cast<float4*>(agg + (size_t)node * H + off) = acc;
+    beg = nbeg, end = nend, e_l = e_n, r_l = r_n;
   }
 }
 
