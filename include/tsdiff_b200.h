@@ -239,15 +239,20 @@ int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float
                  const float* edge_attr, const tsd_pair_mlp_t* mlp, int32_t accumulate, float* ef0,
                  float* edge_inv, int32_t math, tsd_stream_t stream);
 
-/* ---- K7: eq_transform + clip + Langevin update + centring + NaN flag, one launch
- * (replaces models/geometry.py:22-30, models/sampler.py:208-254 LD branch, :260-268 and
- * models/epsnet/dualenc.py:827-849,946-965).
+/* ---- K7: eq_transform + clip + position update + centring + NaN flag, one launch
+ * (replaces models/geometry.py:22-30, models/sampler.py:208-254 -- the `ld` branch :238-244 and the
+ * `ddpm` branch :215-236 --, :260-268 and models/epsnet/dualenc.py:827-849,946-965).
  * Per step k (read from *step_counter, which the kernel post-increments):
  *   score_c = clip_c(eq_transform(inv_c / inv_div, edges selected by mask_c))  for channel c
  *   eps = score_0 + (use1[k] ? w1 * score_1 : 0)
- *   pos = center(pos + step_size[k] * eps / sigma[k] + noise * noise_scale[k])
+ *   LD:   pos = center(pos + step_size[k] * eps / sigma[k] + noise * noise_scale[k])
+ *   DDPM: pos_c = c0 pos; pos0 = c1 pos_c - c2 (-eps); mean = (c3 pos0 + c4 pos_c) / c5;
+ *         pos = center((mean + c6 noise) / c7)     (channel 0 only; every product / sum rounded)
  * noise: external tensor (n_steps, N, 3) if given, else Philox4x32-10 keyed by
  * (seed, step, atom_offset + atom) + Box-Muller.  mask mode: 0 all edges, 1 tab != 0, 2 tab == 0. */
+#define TSD_RULE_LD 0
+#define TSD_RULE_DDPM 1
+
 typedef struct {
   const float* inv;     /* (E) or NULL to disable the channel */
   const int32_t* mask;  /* (E) */
@@ -257,7 +262,10 @@ typedef struct {
 } tsd_score_channel_t;
 
 typedef struct {
-  const float* sched;      /* (num_steps, 4): step_size, sigma, noise_scale, use_channel1 */
+  const float* sched;      /* rule LD:   (num_steps, 4): step_size, sigma, noise_scale, use_channel1
+                            * rule DDPM: (num_steps, 8): sqrt(at), sqrt(1/at), sqrt(1/at - 1), sqrt(atm1) beta_t,
+                            *   sqrt(1 - beta_t) (1 - atm1), 1 - at, mask exp(0.5 log beta_t), sqrt(atm1)
+                            *   (sampler.py:216-236; the caller evaluates them with the reference's fp32 ops) */
   int32_t num_steps;       /* rows of sched / noise; steps beyond it are no-ops */
   int32_t* step_counter;   /* (1) device */
   int32_t* ticket;         /* (1) device scratch, zero-initialised once */
@@ -270,6 +278,7 @@ typedef struct {
   float* traj;             /* (traj_steps, N, 3) or NULL */
   int32_t traj_steps;      /* rows of traj */
   int32_t traj_base_step;  /* traj slot = step - traj_base_step (skipped when out of range) */
+  int32_t rule;            /* TSD_RULE_LD (0) or TSD_RULE_DDPM (1) */
 } tsd_ld_params_t;
 
 int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, float* pos,

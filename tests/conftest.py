@@ -32,6 +32,23 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_ddpm():
+    """Non-default sampler branches (tests/golden/make_golden_ddpm.py)."""
+    return torch.load(os.path.join(GOLDEN, "golden_ddpm.pt"), weights_only=False)
+
+
+# keyword arguments every golden_ddpm case was generated with (make_golden_ddpm.py)
+DDPM_CASES = {
+    "b_rxn0_ddpm20": dict(sampling_type="ddpm"),
+    "b_syn4_ddpm10": dict(sampling_type="ddpm"),
+    "b_rxn0_ddpm_t12": dict(sampling_type="ddpm", denoise_from_time_t=12),
+    "b_rxn0_guess_ld8": dict(sampling_type="ld", denoise_from_time_t=3000, noise_from_time_t=1500),
+    "b_rxn0_guess_ddpm8": dict(sampling_type="ddpm", denoise_from_time_t=600, noise_from_time_t=0),
+    "b_syn4_ld6_clip_pos": dict(sampling_type="ld", clip_pos=20.0),
+}
+
+
+@pytest.fixture(scope="session")
 def rxn0():
     return torch.load(os.path.join(GOLDEN, "rxn0_graph.pt"), weights_only=False)
 

@@ -15,7 +15,7 @@ from tsdiff_b200 import engine as E
 from tsdiff_b200.config import QM9_DEFAULT_MODEL, TRAIN_CONFIG_MODEL
 from tsdiff_b200.synthetic import make_batch, shard_batch
 
-from conftest import graph_for
+from conftest import DDPM_CASES, graph_for
 from helpers import make_model, max_rel_err, oracle_params, rel_err, to_dev
 
 pytestmark = pytest.mark.gpu
@@ -212,6 +212,35 @@ def test_dynamic_sampling_vs_reference_golden(case, seeds, use_graph, golden, rx
     # stated bound (fp32 path): 1e-4 Angstrom over <= 100 steps
     assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4
     assert (pos.cpu() - ref["pos"]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("case", sorted(DDPM_CASES))
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sampler_branches_vs_reference_golden(case, use_graph, golden_ddpm, rxn0, syn4):
+    """The `ddpm` update (sampler.py:215-236, the reference's default sampling_type), the
+    from_ts_guess noising / zero-noise starts (:149-177) and clip_pos, against trajectories
+    produced by the reference's own Python with the same injected noise."""
+    from tsdiff_b200.models.sampler import EnsembleSampler
+    g, ref, kw = graph_for(case, rxn0, syn4), golden_ddpm[case], DDPM_CASES[case]
+    ens = EnsembleSampler([make_model("condensenc", 0, DEV)])
+    d = to_dev(g, DEV)
+    n_steps = ref["noise"].size(0)
+    pos, traj = ens.dynamic_sampling(d["atom_type"], d["r_feat"], d["p_feat"], ref["pos_init"].to(DEV),
+                                     d["bond_index"], d["bond_type"], d["batch"], g["num_graphs"], extend_order=True,
+                                     n_steps=n_steps, step_lr=1e-7, clip=1000, noise=ref["noise"],
+                                     init_noise=ref.get("init_noise"), use_graph=use_graph, **kw)
+    assert len(traj) == n_steps
+    assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4  # Angstrom (fp32 path)
+    assert (pos.cpu() - ref["pos"]).abs().max() < 1e-4
+
+
+def test_unknown_sampling_type_raises(rxn0):
+    from tsdiff_b200.models.sampler import EnsembleSampler
+    ens = EnsembleSampler([make_model("condensenc", 0, DEV)])
+    d = to_dev(rxn0, DEV)
+    with pytest.raises(NotImplementedError):
+        ens.dynamic_sampling(d["atom_type"], d["r_feat"], d["p_feat"], torch.randn(13, 3, device=DEV), d["bond_index"],
+                             d["bond_type"], d["batch"], 1, extend_order=True, n_steps=2, sampling_type="generalized")
 
 
 def test_dynamic_sampling_nan_raises(rxn0):

@@ -11,7 +11,7 @@ from oracle import third_party as tp
 from tsdiff_b200.config import QM9_DEFAULT_MODEL, TRAIN_CONFIG_MODEL
 from tsdiff_b200.synthetic import make_batch
 
-from conftest import GOLDEN, graph_for
+from conftest import DDPM_CASES, GOLDEN, graph_for
 from helpers import make_model, max_rel_err, oracle_params, rel_err
 
 FP32_TOL = 2e-5  # oracle vs reference on CPU: same op graph, only summation-order noise
@@ -125,6 +125,18 @@ def test_ld_trajectory_matches_reference(case, seeds, golden, rxn0, syn4):
                                       ref["pos_init"], g["bond_index"], g["bond_type"], g["batch"], n_steps, 1e-7,
                                       clip=1000, noise=ref["noise"])
     assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4  # Angstrom, positions are O(10)
+    assert (pos - ref["pos"]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("case", sorted(DDPM_CASES))
+def test_sampler_branches_match_reference(case, golden_ddpm, rxn0, syn4):
+    """sampler.py:149-182 starts (from_ts_guess noising, zero-noise, default) and the ddpm update (:215-236)."""
+    g, ref, kw = graph_for(case, rxn0, syn4), golden_ddpm[case], DDPM_CASES[case]
+    ps = [oracle_params(make_model("condensenc", 0))]
+    pos, traj = O.dynamic_sampling(ps, TRAIN_CONFIG_MODEL, g["atom_type"], g["r_feat"], g["p_feat"], ref["pos_init"],
+                                   g["bond_index"], g["bond_type"], g["batch"], ref["noise"].size(0), 1e-7, clip=1000,
+                                   noise=ref["noise"], init_noise=ref.get("init_noise"), **kw)
+    assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4  # Angstrom
     assert (pos - ref["pos"]).abs().max() < 1e-4
 
 

@@ -188,8 +188,10 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
   __syncthreads();
   const int step = sstep;
   if (step < ld.num_steps) {
-    const float step_size = ld.sched[4 * step], sigma = ld.sched[4 * step + 1], nscale = ld.sched[4 * step + 2];
-    const bool use1 = ch1.inv != nullptr && ld.sched[4 * step + 3] != 0.f;
+    const bool ddpm = ld.rule == TSD_RULE_DDPM;
+    const float* sc = ld.sched + (size_t)(ddpm ? 8 : 4) * step;
+    const float step_size = sc[0], sigma = sc[1], nscale = sc[2];
+    const bool use1 = !ddpm && ch1.inv != nullptr && sc[3] != 0.f;
     const int e0 = e.row_ptr[n0], count = e.row_ptr[n0 + n] - e0;  // this graph's edges are contiguous
     const bool staged = count <= smem_edge_cap;
     LdSmem sm;
@@ -220,10 +222,25 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
       } else {
         z = tsd_philox_normal3(ld.seed, step, ld.atom_offset + i);
       }
-      // pos + step_size * eps / sigma + noise * sqrt(2 step_size)   (sampler.py:239-244)
-      float nx = __fadd_rn(__fadd_rn(spos[3 * li], __fdiv_rn(__fmul_rn(step_size, eps.x), sigma)), __fmul_rn(z.x, nscale));
-      float ny = __fadd_rn(__fadd_rn(spos[3 * li + 1], __fdiv_rn(__fmul_rn(step_size, eps.y), sigma)), __fmul_rn(z.y, nscale));
-      float nz = __fadd_rn(__fadd_rn(spos[3 * li + 2], __fdiv_rn(__fmul_rn(step_size, eps.z), sigma)), __fmul_rn(z.z, nscale));
+      float nx, ny, nz;
+      if (ddpm) {
+        // sampler.py:223-236, one rounded operation per reference tensor op
+        const float ev[3] = {-eps.x, -eps.y, -eps.z}, zv[3] = {z.x, z.y, z.z};
+        float out[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float pos_c = __fmul_rn(sc[0], spos[3 * li + d]);
+          const float pos0 = __fsub_rn(__fmul_rn(sc[1], pos_c), __fmul_rn(sc[2], ev[d]));
+          const float mean = __fdiv_rn(__fadd_rn(__fmul_rn(sc[3], pos0), __fmul_rn(sc[4], pos_c)), sc[5]);
+          out[d] = __fdiv_rn(__fadd_rn(mean, __fmul_rn(sc[6], zv[d])), sc[7]);
+        }
+        nx = out[0], ny = out[1], nz = out[2];
+      } else {
+        // pos + step_size * eps / sigma + noise * sqrt(2 step_size)   (sampler.py:239-244)
+        nx = __fadd_rn(__fadd_rn(spos[3 * li], __fdiv_rn(__fmul_rn(step_size, eps.x), sigma)), __fmul_rn(z.x, nscale));
+        ny = __fadd_rn(__fadd_rn(spos[3 * li + 1], __fdiv_rn(__fmul_rn(step_size, eps.y), sigma)), __fmul_rn(z.y, nscale));
+        nz = __fadd_rn(__fadd_rn(spos[3 * li + 2], __fdiv_rn(__fmul_rn(step_size, eps.z), sigma)), __fmul_rn(z.z, nscale));
+      }
       if (isnan(nx) || isnan(ny) || isnan(nz)) atomicOr(ld.nan_flag, 1);
       snew[3 * li] = nx;
       snew[3 * li + 1] = ny;
@@ -264,6 +281,7 @@ extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, f
   TSD_REQUIRE(batch && edges && pos && ch0 && ch0->inv && ld && ld->sched && ld->step_counter && ld->ticket &&
               ld->nan_flag);
   TSD_REQUIRE(batch->max_graph_nodes <= TSD_MAX_GRAPH_NODES);
+  TSD_REQUIRE(ld->rule == TSD_RULE_LD || ld->rule == TSD_RULE_DDPM);
   if (batch->num_graphs == 0) return TSD_OK;
   tsd_score_channel_t off;
   memset(&off, 0, sizeof(off));

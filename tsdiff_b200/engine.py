@@ -415,7 +415,8 @@ class LangevinRunner:
     a device step counter (the score net ignores the time step)."""
 
     def __init__(self, engine, ch0, ch1, sched, pos, noise=None, seed=0, atom_offset=0, clip_pos=None,
-                 keep_traj=True, use_graph=True):
+                 keep_traj=True, use_graph=True, rule=L.RULE_LD):
+        assert sched.size(1) == (8 if rule == L.RULE_DDPM else 4)
         self.engine, self.plan = engine, engine.plan
         dev = self.plan.device
         self.n_steps = sched.size(0)
@@ -435,7 +436,7 @@ class LangevinRunner:
             self.nan_flag.data_ptr(), self.noise.data_ptr() if self.noise is not None else None,
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(atom_offset), float(engine.num_members),
             float(clip_pos) if clip_pos is not None else 0.0,
-            self.traj.data_ptr() if self.traj is not None else None, self.n_steps if keep_traj else 0, 0)
+            self.traj.data_ptr() if self.traj is not None else None, self.n_steps if keep_traj else 0, 0, int(rule))
         self.use_graph = use_graph
         self.graph = None
 
@@ -481,6 +482,28 @@ class LangevinRunner:
         if int(self.nan_flag.item()):
             raise FloatingPointError()
         return self.pos
+
+
+def ddpm_schedule(betas, t_end, n_steps):
+    """(n_steps, 8) coefficient table of the `ddpm` update for i = t_end-1 ... t_end-n_steps and
+    j = i-1 (-1 below the first index), evaluated with the reference's own fp32 tensor expressions
+    (compute_alpha and sampler.py:216-236) on the CPU: sqrt(at), sqrt(1/at), sqrt(1/at - 1),
+    sqrt(atm1) beta_t, sqrt(1 - beta_t) (1 - atm1), 1 - at, mask exp(0.5 log beta_t), sqrt(atm1)."""
+    betas = betas.detach().float().cpu()
+    cum = (1 - torch.cat([torch.zeros(1), betas], dim=0)).cumprod(dim=0)  # compute_alpha, sampler.py:138-141
+    seq = list(range(t_end - n_steps, t_end))
+    seq_next = [-1] + seq[:-1]
+    rows = []
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        t = torch.tensor([i], dtype=torch.long)
+        at = cum.index_select(0, t + 1)
+        atm1 = cum.index_select(0, (torch.ones(1) * j).long() + 1)
+        beta_t = 1 - at / atm1
+        mask = 1 - (t == 0).float()
+        rows.append(torch.cat([at.sqrt(), (1.0 / at).sqrt(), (1.0 / at - 1).sqrt(), atm1.sqrt() * beta_t,
+                               (1 - beta_t).sqrt() * (1 - atm1), 1.0 - at, mask * torch.exp(0.5 * beta_t.log()),
+                               atm1.sqrt()]))
+    return torch.stack(rows).contiguous()
 
 
 def ld_schedule(alphas, n_steps, step_lr, global_start_sigma=float("inf")):

@@ -38,30 +38,44 @@ class EnsembleSampler(nn.Module):
     def dynamic_sampling(self, atom_type, r_feat, p_feat, pos_init, bond_index, bond_type, batch, num_graphs,
                          extend_order, extend_radius=True, n_steps=100, step_lr=0.0000010, clip=1000, clip_pos=None,
                          denoise_from_time_t=None, noise_from_time_t=None, **kwargs):
-        """sampler.py:118-257 for sampling_type='ld'.  Returns (pos on device, list of n_steps
-        CPU (N,3) tensors).  Raises FloatingPointError when a NaN position appears.
-        Keyword-only extras absent from the reference: noise= (n_steps,N,3) tensor used instead
-        of torch.randn_like; seed= Philox seed (default torch.initial_seed()); keep_traj=;
-        atom_offset= global index of the first atom of this shard; use_graph=."""
+        """sampler.py:118-257: the `ld` (:238-244) and `ddpm` (:215-236, the reference's default)
+        updates and the three starts (:149-182: from_ts_guess noising, zero-noise start, default).
+        Returns (pos on device, list of n_steps CPU (N,3) tensors).  Raises FloatingPointError when
+        a NaN position appears.  Keyword-only extras absent from the reference: noise=
+        (n_steps,N,3) tensor used instead of torch.randn_like; init_noise= (N,3) tensor used
+        instead of the torch.randn draw of the from_ts_guess start; seed= Philox seed (default
+        torch.initial_seed()); keep_traj=; atom_offset= global index of the first atom of this
+        shard; use_graph=."""
+        from .. import _lib as L
         sampling_type = kwargs.get("sampling_type", "ddpm")
-        if sampling_type != "ld":
-            raise NotImplementedError("sampling_type %r: only 'ld' is on the hot path (SURVEY.md 8(f)-3)"
-                                      % (sampling_type,))
-        if noise_from_time_t is not None:
-            raise NotImplementedError("from_ts_guess noising (sampler.py:149-167) is SURVEY.md 8(f)-3 scope")
+        if sampling_type not in ("ld", "ddpm"):
+            raise NotImplementedError("sampling_type %r: 'ld' and 'ddpm' are built (SURVEY.md 8(f)-3)" % (sampling_type,))
         eng = self._engine(atom_type, r_feat, p_feat, bond_index, bond_type, batch)
         t_end = self.num_timesteps if denoise_from_time_t is None else int(denoise_from_time_t)
         assert t_end >= n_steps
         sched, sigmas = E.ld_schedule(self.alphas[:t_end], n_steps, step_lr)
         pos = pos_init.detach().to(torch.float32)
-        if denoise_from_time_t is None:
+        if noise_from_time_t is not None:  # sampler.py:149-161
+            assert denoise_from_time_t is not None and denoise_from_time_t >= noise_from_time_t >= 0
+            z0 = kwargs.get("init_noise")
+            if z0 is None:
+                z0 = torch.randn(pos_init.size(), device=pos_init.device)
+            alphas = self.alphas.to(pos.device)
+            alpha_t = alphas[denoise_from_time_t - 1]
+            alpha_s = alphas[noise_from_time_t - 1] if noise_from_time_t != 0 else 1
+            pos = pos + z0.to(pos) * ((1.0 - (alpha_t / alpha_s)) / alpha_t).sqrt()
+        elif denoise_from_time_t is None:
             pos = pos * sigmas[-1].to(pos.device)  # sampler.py:182
         pos = pos.contiguous().clone()
+        rule = L.RULE_LD
+        if sampling_type == "ddpm":
+            sched, rule = E.ddpm_schedule(self.betas, t_end, n_steps), L.RULE_DDPM
         ch0, ch1 = eng.score_channels(clip)
         runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, noise=kwargs.get("noise"),
                                   seed=kwargs.get("seed", torch.initial_seed()),
                                   atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
-                                  keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True))
+                                  keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True),
+                                  rule=rule)
         pos = runner.run()
         traj = list(runner.traj.cpu().unbind(0)) if runner.traj is not None else []
         return pos, traj
