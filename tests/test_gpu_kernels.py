@@ -234,6 +234,47 @@ def test_sampler_branches_vs_reference_golden(case, use_graph, golden_ddpm, rxn0
     assert (pos.cpu() - ref["pos"]).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("save_traj", [False, True])
+def test_sampling_script_body_vs_oracle(save_traj, syn4):
+    """tsdiff_b200.data.sample_batch = the loop body of sampling.py:169-225 (collate, sample, alpha-scaled
+    trajectory, per-reaction results) against the oracle sampler on the same noise."""
+    from tsdiff_b200.data import Batch, Data, count_nodes_per_graph, sample_batch
+    from tsdiff_b200.models.sampler import EnsembleSampler
+    sizes, off, data = [10, 17, 25, 12], 0, []
+    for k, n in enumerate(sizes):
+        sel = (syn4["bond_index"][0] >= off) & (syn4["bond_index"][0] < off + n)
+        data.append(count_nodes_per_graph(Data(
+            atom_type=syn4["atom_type"][off:off + n], r_feat=syn4["r_feat"][off:off + n],
+            p_feat=syn4["p_feat"][off:off + n], pos=syn4["pos_init"][off:off + n],
+            edge_index=syn4["bond_index"][:, sel] - off, edge_type=syn4["bond_type"][sel], smiles="rxn%d" % k)))
+        off += n
+    m = make_model("condensenc", 0, DEV)
+    ens = EnsembleSampler([m])
+    n_steps = 6
+    gen = torch.Generator().manual_seed(77)
+    noise = torch.randn(n_steps, 64, 3, generator=gen)
+    pos_init = syn4["pos_init"]
+    batch = Batch.from_data_list(data).to(DEV)
+    results = sample_batch(ens, batch, n_steps=n_steps, step_lr=1e-7, clip=1000.0, sampling_type="ld",
+                           save_traj=save_traj, pos_init=pos_init.to(DEV), noise=noise)
+    ref_pos, ref_traj = O.dynamic_sampling(
+        [oracle_params(m)], TRAIN_CONFIG_MODEL, syn4["atom_type"], syn4["r_feat"], syn4["p_feat"], pos_init,
+        syn4["bond_index"], syn4["bond_type"], syn4["batch"], n_steps, 1e-7, clip=1000, noise=noise)
+    assert len(results) == 4 and [r.smiles for r in results] == ["rxn0", "rxn1", "rxn2", "rxn3"]
+    alphas = oracle_params(m)["alphas"]
+    scale = alphas[alphas.numel() - n_steps:].flip(0).view(-1, 1, 1).sqrt()
+    off = 0
+    for r, n in zip(results, sizes):
+        assert not r.pos_gen.is_cuda and r.atom_type.numel() == n
+        if save_traj:
+            want = (torch.stack(ref_traj) * scale)[:, off:off + n]
+            assert r.pos_gen.shape == (n_steps, n, 3)
+        else:
+            want = ref_pos[off:off + n]
+        assert (r.pos_gen - want).abs().max() < 1e-4
+        off += n
+
+
 def test_unknown_sampling_type_raises(rxn0):
     from tsdiff_b200.models.sampler import EnsembleSampler
     ens = EnsembleSampler([make_model("condensenc", 0, DEV)])
