@@ -247,7 +247,8 @@ def kernel_rooflines(args, eng, peaks, device):
     from tsdiff_b200 import _lib as L
     lib = L.load()
     plan, h = eng.plan, eng.hidden
-    e = plan.edge_count()
+    e = plan.work_count()  # rows of the per-edge kernels: unordered pairs (path B) or directed edges
+    e_dir = plan.edge_count()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     # L2 flush = write pass + read pass over 256 MiB each: the read pass evicts the dirty lines of
     # the write pass, so their write-back does not compete with the timed kernel
@@ -275,7 +276,7 @@ def kernel_rooflines(args, eng, peaks, device):
             ts.append(t0.elapsed_time(t1) * 1e-3)
         return sum(ts) / len(ts)
 
-    t_f = timed(lambda: L.check(lib.tsd_filter_network(C.byref(plan.c_batch), C.byref(plan.c_edges), L.ptr(x),
+    t_f = timed(lambda: L.check(lib.tsd_filter_network(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), L.ptr(x),
                                                        C.byref(blocks[0]), L.ptr(tmp), L.ptr(out), math, stream),
                                 "tsd_filter_network"))
     flops = 2 * 2.0 * e * h * h
@@ -289,10 +290,11 @@ def kernel_rooflines(args, eng, peaks, device):
               "algorithmic_bytes": 2 * e * h * 4 + 2 * h * h * 4}
     x1 = ws.node[1]
     agg = ws.node[2]
-    t_agg = timed(lambda: L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_batch), C.byref(plan.c_edges), h, L.ptr(x1),
+    t_agg = timed(lambda: L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), h, L.ptr(x1),
                                                            L.ptr(out), L.ptr(agg), stream), "tsd_cfconv_aggregate"))
     n = plan.num_nodes
-    nbytes = e * h * 4 + 2 * n * h * 4 + e * 8 + (n + 1) * 4
+    # every directed in-edge reads one filter row (of its pair) and one x1 row's worth of index data
+    nbytes = e * h * 4 + 2 * n * h * 4 + e_dir * 8 + (n + 1) * 4
     hbm = {"bound": "hbm", "kernel": "k_cfconv_aggregate", "achieved": nbytes / t_agg / 1e9, "peak": peaks["hbm"],
            "unit": "GB/s", "frac": nbytes / t_agg / 1e9 / peaks["hbm"], "traffic": traffic.get("k_cfconv_aggregate"),
            "peak_source": peaks["source"], "us_per_launch": t_agg * 1e6, "algorithmic_bytes": nbytes}
@@ -407,7 +409,10 @@ def run_ours(args):
            "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "tf32", "data": "synthetic",
            "config": dict(workload_config(args, world), l2="flushed between timed trajectories (256 MiB write)",
                           edges_late_trajectory=mean_edges, nodes=int(data["atom_type"].numel()),
-                          edge_capacity=eng.plan.edge_capacity),
+                          edge_capacity=eng.plan.edge_capacity,
+                          network_rows_late_trajectory=eng.plan.work_count(),
+                          dedup="per-edge networks run once per unordered atom pair (both directions are "
+                                "bit-identical)" if eng.plan.upairs else "none"),
            "us_per_eps_step": ms_per_step * 1e3 / args.ld_steps,
            "gpu_launches": int(launches_per_ld_step) * args.ld_steps * args.steps,
            "launches_per_ld_step": int(launches_per_ld_step), "clocks": clock_info, "e2e": e2e,

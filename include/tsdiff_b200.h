@@ -79,6 +79,23 @@ typedef struct {
   int32_t* in_eid;     /* (E) edge ids sorted by (col, row) */
   int32_t* in_src;     /* (E) source node of in_eid[k] (= row[in_eid[k]]), saves a dependent load */
   int32_t* graph_count;/* (G) scratch: edges per graph */
+  /* Undirected pair list (optional; num_upairs == NULL skips it).  The directed edges (i,j) and
+   * (j,i) have bit-identical length and -- for a symmetric bond list -- table values, so everything
+   * the networks compute per edge (edge embedding, CFConv filters, the pair MLP) is identical for
+   * both directions.  K2 also emits each unordered pair {i<j} that has at least one directed edge
+   * once, sorted by (i, j), plus the pair id of every directed edge / in-CSR slot; the per-edge
+   * kernels then run over U ~ E/2 rows (pass a view whose num_edges, row, col, length, tab0, tab1, in_eid
+   * are num_upairs, u_row, u_col, u_length, u_tab0, u_tab1, in_upair) and consumers index results
+   * through edge_upair. */
+  int32_t* num_upairs; /* (1) U */
+  int32_t* u_row;      /* (U_cap) i, the smaller node; U_cap = sum_g n_g (n_g - 1) / 2 */
+  int32_t* u_col;      /* (U_cap) j */
+  float* u_length;     /* (U_cap) */
+  int32_t* u_tab0;     /* (U_cap) table 0 value at (i, j) */
+  int32_t* u_tab1;     /* (U_cap) */
+  int32_t* edge_upair; /* (E) pair id of directed edge e */
+  int32_t* in_upair;   /* (E) pair id of in-CSR slot k (= edge_upair[in_eid[k]]) */
+  int32_t* graph_ucount;/* (G) scratch: pairs per graph */
 } tsd_edges_t;
 
 const char* tsd_error_string(int code);
@@ -254,11 +271,12 @@ int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float
 #define TSD_RULE_DDPM 1
 
 typedef struct {
-  const float* inv;     /* (E) or NULL to disable the channel */
+  const float* inv;     /* (E) -- or (U) when inv_index is given -- or NULL to disable the channel */
   const int32_t* mask;  /* (E) */
   int32_t mask_mode;
   float clip;           /* <= 0: no clipping */
   float weight;
+  const int32_t* inv_index; /* (E) or NULL: score of edge e = inv[inv_index[e]] (edges->edge_upair) */
 } tsd_score_channel_t;
 
 typedef struct {

@@ -466,3 +466,40 @@ def test_stress_shape_forward_vs_oracle():
     keys = set((ridx[0] * n + ridx[1]).tolist())
     assert any((int(c) * n + int(r)) not in keys for r, c in ridx.t().tolist()), "cap should make the graph asymmetric"
     assert rel_err(ei, rei) < EPS_TOL and max_rel_err(ei, rei) < EPS_TOL
+
+
+@pytest.mark.parametrize("name,scale,cutoff", [("rxn0", 1.0, 10.0), ("syn4", 3.0, 10.0), ("syn4", 8.0, 10.0), ("stress", 4.0, 15.0)])
+def test_undirected_pair_list_consistent(name, scale, cutoff, rxn0, syn4):
+    """K2's unordered pair list: one entry per {i<j} with at least one directed edge, sorted, with the
+    bit-identical length / table values of its directions (also when the neighbour cap makes the directed
+    graph asymmetric), and edge_upair / in_upair mapping every directed edge / in-slot to its pair."""
+    g = make_batch(5, seed=9, min_atoms=55, max_atoms=65) if name == "stress" else graph_for(name, rxn0, syn4)
+    torch.manual_seed(12)
+    pos = torch.randn(g["atom_type"].numel(), 3) * scale
+    d = to_dev(g, DEV)
+    plan = E.BatchPlan(0, d["batch"], d["bond_index"], d["bond_type"], 4, 3, upairs=True)
+    assert plan.upairs
+    plan.build_edges(pos.to(DEV).contiguous(), cutoff)
+    e, idx = _plan_edges(plan)
+    u = plan.work_count()
+    n = plan.num_nodes
+    urow, ucol = plan.u_row[:u].long().cpu(), plan.u_col[:u].long().cpu()
+    lo, hi = torch.minimum(idx[0], idx[1]), torch.maximum(idx[0], idx[1])
+    want = torch.unique(lo * n + hi)  # sorted
+    assert torch.equal(urow * n + ucol, want)
+    up = plan.edge_upair[:e].long().cpu()
+    assert torch.equal(urow[up], lo) and torch.equal(ucol[up], hi)
+    assert torch.equal(plan.u_length[:u].cpu()[up], plan.length[:e].cpu())          # bit-identical
+    assert torch.equal(plan.u_tab0[:u].cpu()[up], plan.tab0[:e].cpu())
+    assert torch.equal(plan.u_tab1[:u].cpu()[up], plan.tab1[:e].cpu())
+    assert torch.equal(plan.in_upair[:e].cpu().long(), up[plan.in_eid[:e].long().cpu()])
+    if name == "stress":
+        assert u * 2 > e, "expected one-directional edges under the neighbour cap"
+
+
+def test_asymmetric_bond_list_disables_pair_sharing(syn4):
+    d = to_dev(syn4, DEV)
+    keep = torch.ones(d["bond_index"].size(1), dtype=torch.bool, device=DEV)
+    keep[0] = False  # drop one direction of a bond: tables are no longer symmetric
+    plan = E.BatchPlan(0, d["batch"], d["bond_index"][:, keep], d["bond_type"][keep], 4, 3, upairs=True)
+    assert not plan.upairs and plan.c_work_edges is plan.c_edges

@@ -30,7 +30,10 @@ class Batch(C.Structure):
 class Edges(C.Structure):
     _fields_ = [("num_edges", C.c_void_p), ("row", C.c_void_p), ("col", C.c_void_p), ("length", C.c_void_p),
                 ("tab0", C.c_void_p), ("tab1", C.c_void_p), ("in_b", C.c_void_p), ("row_ptr", C.c_void_p),
-                ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p), ("in_src", C.c_void_p), ("graph_count", C.c_void_p)]
+                ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p), ("in_src", C.c_void_p), ("graph_count", C.c_void_p),
+                ("num_upairs", C.c_void_p), ("u_row", C.c_void_p), ("u_col", C.c_void_p), ("u_length", C.c_void_p),
+                ("u_tab0", C.c_void_p), ("u_tab1", C.c_void_p), ("edge_upair", C.c_void_p), ("in_upair", C.c_void_p),
+                ("graph_ucount", C.c_void_p)]
 
 
 class EdgeEncoder(C.Structure):
@@ -53,7 +56,7 @@ class PairMlp(C.Structure):
 
 class ScoreChannel(C.Structure):
     _fields_ = [("inv", C.c_void_p), ("mask", C.c_void_p), ("mask_mode", C.c_int32), ("clip", C.c_float),
-                ("weight", C.c_float)]
+                ("weight", C.c_float), ("inv_index", C.c_void_p)]
 
 
 class LdParams(C.Structure):

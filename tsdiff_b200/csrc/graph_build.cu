@@ -236,6 +236,26 @@ __device__ __forceinline__ int k2_row_popc(const unsigned* m, int W) {
   return s;
 }
 
+// bits j > r of word w of row r: the upper triangle of the pair matrix
+__device__ __forceinline__ unsigned k2_upper_mask(int r, int w) {
+  const int rw = r >> 5;
+  if (w < rw) return 0u;
+  if (w > rw) return 0xffffffffu;
+  return ~((2u << (r & 31)) - 1u);  // r & 31 == 31: 2u << 31 wraps to 0 -> mask 0
+}
+
+// word w of the undirected pair mask of row r: j > r with (r -> j) or (j -> r) in graph a
+__device__ __forceinline__ unsigned k2_upair_word(const GraphTile& t, int r, int w) {
+  return (t.out_a[r * t.W + w] | t.in_a[r * t.W + w]) & k2_upper_mask(r, w);
+}
+
+// number of set bits of the row mask below column c
+__device__ __forceinline__ int k2_rank_below(const unsigned* row_mask, int c) {
+  int rank = 0;
+  for (int w2 = 0; w2 < (c >> 5); ++w2) rank += __popc(row_mask[w2]);
+  return rank + __popc(row_mask[c >> 5] & ((1u << (c & 31)) - 1u));
+}
+
 __device__ int k2_block_sum(int v, int* s_red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TSD_FULL_MASK, v, o);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,15 +269,24 @@ __device__ int k2_block_sum(int v, int* s_red) {
 
 // pass 1: edges per graph
 __global__ void __launch_bounds__(256) k_edge_count(tsd_batch_t b, const float* __restrict__ pos, float r2, int cap,
-                                                    const int* __restrict__ table0, int* __restrict__ graph_count) {
+                                                    const int* __restrict__ table0, int* __restrict__ graph_count,
+                                                    int* __restrict__ graph_ucount) {
   extern __shared__ unsigned smem_u[];
   __shared__ int s_red[8];
   GraphTile t = k2_tile(b, blockIdx.x, smem_u);
   k2_build_masks(t, pos, r2, cap, table0);
-  int local = 0;
-  for (int r = threadIdx.x; r < t.n; r += blockDim.x) local += k2_row_popc(t.out_a + r * t.W, t.W);
+  int local = 0, ulocal = 0;
+  for (int r = threadIdx.x; r < t.n; r += blockDim.x) {
+    local += k2_row_popc(t.out_a + r * t.W, t.W);
+    if (graph_ucount)
+      for (int w = 0; w < t.W; ++w) ulocal += __popc(k2_upair_word(t, r, w));
+  }
   int tot = k2_block_sum(local, s_red);
   if (threadIdx.x == 0) graph_count[blockIdx.x] = tot;
+  if (graph_ucount) {
+    int utot = k2_block_sum(ulocal, s_red);
+    if (threadIdx.x == 0) graph_ucount[blockIdx.x] = utot;
+  }
 }
 
 // exclusive scan of deg(r) over the rows of one graph by one warp
@@ -288,15 +317,27 @@ __global__ void __launch_bounds__(256) k_edge_emit(tsd_batch_t b, const float* _
   GraphTile t = k2_tile(b, g, smem_u);
   int* row_off = reinterpret_cast<int*>(t.in_a + b.max_graph_nodes * t.W);
   int* in_off = row_off + b.max_graph_nodes + 1;
+  int* u_off = in_off + b.max_graph_nodes + 1;
+  unsigned* pm = reinterpret_cast<unsigned*>(u_off + b.max_graph_nodes + 1);  // n*W undirected pair masks
   k2_build_masks(t, pos, r2, cap, table0);
+  const bool upairs = e.num_upairs != nullptr;
 
-  int part = 0;
-  for (int i = threadIdx.x; i < g; i += blockDim.x) part += e.graph_count[i];
+  int part = 0, upart = 0;
+  for (int i = threadIdx.x; i < g; i += blockDim.x) {
+    part += e.graph_count[i];
+    if (upairs) upart += e.graph_ucount[i];
+  }
   const int gbase = k2_block_sum(part, s_red);
+  const int ubase = upairs ? k2_block_sum(upart, s_red) : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int n = t.n, W = t.W;
+  if (upairs) {
+    for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) pm[idx] = k2_upair_word(t, idx / W, idx % W);
+    __syncthreads();
+  }
   if (warp == 0) k2_warp_scan_rows(t.out_a, n, W, row_off);
   if (warp == 1) k2_warp_scan_rows(t.in_a, n, W, in_off);
+  if (warp == 2 && upairs) k2_warp_scan_rows(pm, n, W, u_off);
   __syncthreads();
   for (int r = threadIdx.x; r < n; r += blockDim.x) {
     e.row_ptr[t.n0 + r] = gbase + row_off[r];
@@ -307,8 +348,31 @@ __global__ void __launch_bounds__(256) k_edge_emit(tsd_batch_t b, const float* _
     e.row_ptr[b.num_nodes] = total;
     e.in_ptr[b.num_nodes] = total;
     e.num_edges[0] = total;
+    if (upairs) e.num_upairs[0] = ubase + u_off[n];
   }
   const unsigned lt = tsd_lanemask_lt();
+  // undirected pairs {i < j}, warp per row i: the same length / table expressions as the directed
+  // edges below, so a pair's values are bit-identical to those of both of its directions
+  if (upairs) {
+    for (int i = warp; i < n; i += nwarps) {
+      float ix = t.spos[3 * i], iy = t.spos[3 * i + 1], iz = t.spos[3 * i + 2];
+      int running = ubase + u_off[i];
+      for (int w = 0; w < W; ++w) {
+        unsigned bits = pm[i * W + w];
+        if ((bits >> lane) & 1u) {
+          int j = w * 32 + lane;
+          int uid = running + __popc(bits & lt);
+          e.u_row[uid] = t.n0 + i;
+          e.u_col[uid] = t.n0 + j;
+          e.u_length[uid] = __fsqrt_rn(tsd_dist2(ix, iy, iz, t.spos[3 * j], t.spos[3 * j + 1], t.spos[3 * j + 2]));
+          int pidx = t.base + i * n + j;
+          e.u_tab0[uid] = table0[pidx];
+          if (e.u_tab1) e.u_tab1[uid] = table1 ? table1[pidx] : 0;
+        }
+        running += __popc(bits);
+      }
+    }
+  }
   // out-edges, warp per row
   for (int r = warp; r < n; r += nwarps) {
     float rx = t.spos[3 * r], ry = t.spos[3 * r + 1], rz = t.spos[3 * r + 2];
@@ -330,6 +394,10 @@ __global__ void __launch_bounds__(256) k_edge_emit(tsd_batch_t b, const float* _
           bool rad_out = (t.radin[c * W + (r >> 5)] >> (r & 31)) & 1u;
           e.in_b[eid] = tab1_is_graph ? ((t1 != 0 || rad_out) ? 1 : 0) : 1;
         }
+        if (upairs) {
+          const int i = min(r, c), j = max(r, c);
+          e.edge_upair[eid] = ubase + u_off[i] + k2_rank_below(pm + i * W, j);
+        }
       }
       running += __popc(bits);
     }
@@ -349,6 +417,10 @@ __global__ void __launch_bounds__(256) k_edge_emit(tsd_batch_t b, const float* _
         rank += __popc(orow[c >> 5] & ((1u << (c & 31)) - 1u));
         e.in_eid[k] = gbase + row_off[r] + rank;
         e.in_src[k] = t.n0 + r;
+        if (upairs) {
+          const int i = min(r, c), j = max(r, c);
+          e.in_upair[k] = ubase + u_off[i] + k2_rank_below(pm + i * W, j);
+        }
       }
       running += __popc(bits);
     }
@@ -369,8 +441,13 @@ extern "C" int tsd_edge_build(const tsd_batch_t* batch, const float* pos, double
   // torch_cluster squares the double radius on the host and casts to float
   float r2 = (float)(cutoff * cutoff);
   int cap = max_neighbors + 1;  // radius_graph(loop=False) asks for max_num_neighbors + 1 incl. self
-  size_t smem = (size_t)(3 * nmax + 3 * nmax * W + 2 * (nmax + 1)) * sizeof(unsigned);
-  k_edge_count<<<batch->num_graphs, 256, smem, s>>>(*batch, pos, r2, cap, table0, edges->graph_count);
+  const bool upairs = edges->num_upairs != nullptr;
+  if (upairs)
+    TSD_REQUIRE(edges->u_row && edges->u_col && edges->u_length && edges->u_tab0 && edges->edge_upair && edges->in_upair &&
+                edges->graph_ucount);
+  size_t smem = (size_t)(3 * nmax + 4 * nmax * W + 3 * (nmax + 1)) * sizeof(unsigned);
+  k_edge_count<<<batch->num_graphs, 256, smem, s>>>(*batch, pos, r2, cap, table0, edges->graph_count,
+                                                    upairs ? edges->graph_ucount : nullptr);
   TSD_LAUNCH_CHECK();
   k_edge_emit<<<batch->num_graphs, 256, smem, s>>>(*batch, pos, r2, cap, table0, table1, tab1_is_graph, *edges);
   TSD_LAUNCH_CHECK();

@@ -74,7 +74,7 @@ __device__ float3 tsd_node_score(const tsd_score_channel_t& ch, const tsd_edges_
     if (!tsd_edge_selected(ch, k)) continue;
     int c = e.col[k] - n0;
     float inv_len = __fdiv_rn(1.0f, e.length[k]);
-    float s = __fdiv_rn(ch.inv[k], inv_div);
+    float s = __fdiv_rn(ch.inv[ch.inv_index ? ch.inv_index[k] : k], inv_div);
     ax = __fadd_rn(ax, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(px, spos[3 * c])), s));
     ay = __fadd_rn(ay, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(py, spos[3 * c + 1])), s));
     az = __fadd_rn(az, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(pz, spos[3 * c + 2])), s));
@@ -84,7 +84,7 @@ __device__ float3 tsd_node_score(const tsd_score_channel_t& ch, const tsd_edges_
     if (!tsd_edge_selected(ch, id)) continue;
     int r = e.row[id] - n0;
     float inv_len = __fdiv_rn(1.0f, e.length[id]);
-    float s = __fdiv_rn(ch.inv[id], inv_div);
+    float s = __fdiv_rn(ch.inv[ch.inv_index ? ch.inv_index[id] : id], inv_div);
     bx = __fadd_rn(bx, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r], px)), s));
     by = __fadd_rn(by, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 1], py)), s));
     bz = __fadd_rn(bz, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 2], pz)), s));
@@ -145,7 +145,7 @@ __device__ __forceinline__ void k7_edge_terms(const tsd_score_channel_t& ch, con
     if (tsd_edge_selected(ch, id)) {
       const int r = e.row[id] - n0, c = e.col[id] - n0;
       const float inv_len = __fdiv_rn(1.0f, e.length[id]);
-      const float s = __fdiv_rn(ch.inv[id], inv_div);
+      const float s = __fdiv_rn(ch.inv[ch.inv_index ? ch.inv_index[id] : id], inv_div);
       tx = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r], spos[3 * c])), s);
       ty = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 1], spos[3 * c + 1])), s);
       tz = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 2], spos[3 * c + 2])), s);

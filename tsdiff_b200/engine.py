@@ -27,7 +27,7 @@ class BatchPlan:
     graph offsets, the bond-order pair tables (K1) and the capacity-sized edge arrays that
     K2 refills every step.  mode 0 = TS / condensenc tables, mode 1 = dualenc tables."""
 
-    def __init__(self, mode, batch, bond_index, bond_type, order_a, order_b=0, ts_decode=False):
+    def __init__(self, mode, batch, bond_index, bond_type, order_a, order_b=0, ts_decode=False, upairs=False):
         lib = L.load()
         _require_cuda(batch, "batch")
         dev = batch.device
@@ -91,9 +91,56 @@ class BatchPlan:
         self.in_eid = torch.zeros(cap, **i32)
         self.in_src = torch.zeros(cap, **i32)
         self.graph_count = torch.zeros(max(g, 1), **i32)
-        self.c_edges = L.Edges(*[t.data_ptr() for t in (
-            self.num_edges, self.row, self.col, self.length, self.tab0, self.tab1, self.in_b, self.row_ptr,
-            self.in_ptr, self.in_eid, self.in_src, self.graph_count)])
+        # ---- undirected pair list: the per-edge networks run once per unordered pair (the two directions
+        # of an edge have bit-identical length and, for symmetric pair tables, types)
+        self.upair_capacity = int((counts_h * (counts_h - 1)).sum()) // 2 if g else 0
+        import os
+        self.upairs = bool(upairs) and os.environ.get("TSD_UPAIRS", "1") != "0" and self._tables_symmetric()
+        fields = [self.num_edges, self.row, self.col, self.length, self.tab0, self.tab1, self.in_b, self.row_ptr,
+                  self.in_ptr, self.in_eid, self.in_src, self.graph_count]
+        if self.upairs:
+            ucap = max(self.upair_capacity, 1)
+            self.num_upairs = torch.zeros(1, **i32)
+            self.u_row = torch.zeros(ucap, **i32)
+            self.u_col = torch.zeros(ucap, **i32)
+            self.u_length = torch.ones(ucap, dtype=torch.float32, device=dev)
+            self.u_tab0 = torch.zeros(ucap, **i32)
+            self.u_tab1 = torch.zeros(ucap, **i32)
+            self.edge_upair = torch.zeros(cap, **i32)
+            self.in_upair = torch.zeros(cap, **i32)
+            self.graph_ucount = torch.zeros(max(g, 1), **i32)
+            fields += [self.num_upairs, self.u_row, self.u_col, self.u_length, self.u_tab0, self.u_tab1,
+                       self.edge_upair, self.in_upair, self.graph_ucount]
+            self.c_edges = L.Edges(*[t.data_ptr() for t in fields])
+            # what the per-edge kernels see: one row per unordered pair; the in-CSR still walks the DIRECTED
+            # in-edges of every node but addresses the pair's row (in_upair in the in_eid slot)
+            self.c_work_edges = L.Edges(*[t.data_ptr() for t in (
+                self.num_upairs, self.u_row, self.u_col, self.u_length, self.u_tab0, self.u_tab1, self.in_b,
+                self.row_ptr, self.in_ptr, self.in_upair, self.in_src, self.graph_count)])
+            self.c_work_batch = L.Batch(n, g, self.max_graph_nodes, self.upair_capacity, self.graph_ptr.data_ptr(),
+                                        self.pair_ptr.data_ptr(), self.node_graph.data_ptr())
+            self.work_capacity, self.work_tab0, self.work_tab1 = self.upair_capacity, self.u_tab0, self.u_tab1
+        else:
+            self.c_edges = L.Edges(*[t.data_ptr() for t in fields])
+            self.c_work_edges, self.c_work_batch = self.c_edges, self.c_batch
+            self.work_capacity, self.work_tab0, self.work_tab1 = self.edge_capacity, self.tab0, self.tab1
+
+    def _tables_symmetric(self):
+        """True when both pair tables equal their per-reaction transposes (a symmetric bond list, what
+        datasets.py:495-498 produces).  Position independent: checked once per batch."""
+        c = self.counts
+        if c.numel() == 0:
+            return True
+        n_of = torch.repeat_interleave(c, c * c)                         # n_g of every table entry
+        base = torch.repeat_interleave(self.pair_ptr[:-1].cpu().long(), c * c)
+        local = torch.arange(int((c * c).sum())) - base
+        i, j = local // n_of, local % n_of
+        perm = (base + j * n_of + i).to(self.device)
+        return bool(torch.equal(self.table_a, self.table_a[perm]) and torch.equal(self.table_b, self.table_b[perm]))
+
+    def work_count(self):
+        """Rows the per-edge kernels process (unordered pairs, or directed edges).  Synchronises."""
+        return int(self.num_upairs[0].item()) if self.upairs else self.edge_count()
 
     def build_edges(self, pos, cutoff, max_neighbors=32):
         """K2: refill the edge list for the current positions (no sync)."""
@@ -114,10 +161,10 @@ class _Scratch:
         dev = plan.device
         # the library states what its kernel sequence needs (tsd_workspace_bytes); keep the two in step
         ne, nn = C.c_int32(), C.c_int32()
-        L.check(L.load().tsd_workspace_bytes(plan.num_nodes, plan.edge_capacity, hidden, network, L.MATH[math], None, None,
+        L.check(L.load().tsd_workspace_bytes(plan.num_nodes, plan.work_capacity, hidden, network, L.MATH[math], None, None,
                                              C.byref(ne), C.byref(nn)), "tsd_workspace_bytes")
         assert ne.value == n_edge_bufs and nn.value == n_node_bufs + (2 if math == "tf32" else 0), (ne.value, nn.value)
-        cap = max(plan.edge_capacity, 1)
+        cap = max(plan.work_capacity, 1)
         self.edge = [torch.empty(cap, hidden, dtype=torch.float32, device=dev) for _ in range(n_edge_bufs)]
         self.node = [torch.empty(max(plan.num_nodes, 1), hidden, dtype=torch.float32, device=dev)
                      for _ in range(n_node_bufs)]
@@ -232,7 +279,7 @@ class CondensedScoreEngine:
         for m in self.models:
             if next(m.parameters()).device != batch.device:
                 raise L.TsdError("model parameters and inputs must live on the same CUDA device")
-        self.plan = BatchPlan(0, batch, bond_index, bond_type, int(cfg.edge_order), int(cfg.pred_edge_order))
+        self.plan = BatchPlan(0, batch, bond_index, bond_type, int(cfg.edge_order), int(cfg.pred_edge_order), upairs=True)
         self.two_graphs = int(cfg.edge_order) != int(cfg.pred_edge_order)
         plan = self.plan
         h = int(cfg.hidden_dim)
@@ -242,7 +289,7 @@ class CondensedScoreEngine:
         self.ws = _Scratch(plan, h, 7, 4, 0, math)
         self.side = torch.cuda.Stream(device=plan.device)  # second-graph edge embedding runs beside the encoder
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
-        self.edge_inv = torch.zeros(max(plan.edge_capacity, 1), dtype=torch.float32, device=plan.device)
+        self.edge_inv = torch.zeros(max(plan.work_capacity, 1), dtype=torch.float32, device=plan.device)
         atom_type = atom_type.to(torch.long).contiguous()
         r_feat = r_feat.to(torch.long).contiguous()
         p_feat = p_feat.to(torch.long).contiguous()
@@ -265,21 +312,21 @@ class CondensedScoreEngine:
         over members, on the edges of graph a; consumers select graph b with plan.in_b)."""
         lib = L.load()
         plan, ws, s = self.plan, self.ws, _stream()
-        b, e = C.byref(plan.c_batch), C.byref(plan.c_edges)
+        b, e = C.byref(plan.c_work_batch), C.byref(plan.c_work_edges)  # rows = unordered pairs when plan.upairs
         d_emb, tmp, ea1, ea2, ef0, ef1, tmp2 = ws.edge
         hbuf, nf0, nf1, nf2 = ws.node
         plan.build_edges(pos, self.cutoff)
         main = torch.cuda.current_stream()
         for mi, mem in enumerate(self.members):
             enc = C.byref(mem["enc"])
-            L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab0), enc, 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea1),
+            L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.work_tab0), enc, 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea1),
                                        self.math, s), "tsd_edge_embed")
             if self.two_graphs:
                 # the pred_edge_order graph's edge embedding only needs d_emb: fork it onto a side
                 # stream (a graph branch under capture) so it fills the SMs the encoder leaves idle
                 self.side.wait_stream(main)
                 with torch.cuda.stream(self.side):
-                    L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp2), L.ptr(ea2),
+                    L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.work_tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp2), L.ptr(ea2),
                                                self.math, _stream()), "tsd_edge_embed")
                 ea_out = ea2
             else:
@@ -295,8 +342,15 @@ class CondensedScoreEngine:
 
     def score_channels(self, clip):
         ch0 = L.ScoreChannel(self.edge_inv.data_ptr(), self.plan.in_b.data_ptr(), 1 if self.two_graphs else 0,
-                             float(clip) if clip is not None else 0.0, 1.0)
+                             float(clip) if clip is not None else 0.0, 1.0,
+                             self.plan.edge_upair.data_ptr() if self.plan.upairs else None)
         return ch0, None
+
+    def edge_inv_directed(self, e):
+        """edge_inv (sum over members) of the first e directed edges."""
+        if self.plan.upairs:
+            return self.edge_inv[self.plan.edge_upair[:e].long()]
+        return self.edge_inv[:e]
 
     @property
     def num_members(self):

@@ -64,7 +64,7 @@ def condensed_outputs(eng, return_edges=True, divide=1):
     plan = eng.plan
     e = plan.edge_count()
     sel = plan.in_b[:e].bool() if eng.two_graphs else torch.ones(e, dtype=torch.bool, device=plan.device)
-    edge_inv = eng.edge_inv[:e][sel].unsqueeze(-1)
+    edge_inv = eng.edge_inv_directed(e)[sel].unsqueeze(-1)
     if divide != 1:
         edge_inv = edge_inv / divide
     if not return_edges:
