@@ -322,19 +322,23 @@ class CondensedScoreEngine:
             L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.work_tab0), enc, 0, L.ptr(d_emb), L.ptr(tmp), L.ptr(ea1),
                                        self.math, s), "tsd_edge_embed")
             if self.two_graphs:
-                # the pred_edge_order graph's edge embedding only needs d_emb: fork it onto a side
-                # stream (a graph branch under capture) so it fills the SMs the encoder leaves idle
-                self.side.wait_stream(main)
+                fork = torch.cuda.Event()
+                fork.record(main)
+            L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
+                                           L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
+                                           L.ptr(self.nf_pool), self.nf_pool_count, self.math, s),
+                    "tsd_schnet_encoder")
+            if self.two_graphs:
+                # the pred_edge_order graph's edge embedding only needs d_emb and is only read by the pair
+                # MLP: a side stream (a graph branch under capture) lets it fill the SMs the encoder leaves
+                # idle.  It is ENQUEUED after the encoder so the first filter kernel is not queued behind it.
+                self.side.wait_event(fork)
                 with torch.cuda.stream(self.side):
                     L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.work_tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp2), L.ptr(ea2),
                                                self.math, _stream()), "tsd_edge_embed")
                 ea_out = ea2
             else:
                 ea_out = ea1
-            L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
-                                           L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                           L.ptr(self.nf_pool), self.nf_pool_count, self.math, s),
-                    "tsd_schnet_encoder")
             if self.two_graphs:
                 main.wait_stream(self.side)
             L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_out), C.byref(mem["pair"]), 1 if mi > 0 else 0,
