@@ -378,7 +378,7 @@ class DualScoreEngine:
         _require_cuda(atom_type, "atom_type")
         _require_cuda(batch, "batch")
         self.ts = bool(getattr(model, "TS", False))
-        self.plan = BatchPlan(1, batch, bond_index, bond_type, int(cfg.edge_order), 0, ts_decode=self.ts)
+        self.plan = BatchPlan(1, batch, bond_index, bond_type, int(cfg.edge_order), 0, ts_decode=self.ts, upairs=True)
         plan = self.plan
         h = int(cfg.hidden_dim)
         self.hidden = h
@@ -386,7 +386,7 @@ class DualScoreEngine:
         self.ws = _Scratch(plan, h, 7, 7, 1, math)
         self.side = torch.cuda.Stream(device=plan.device)  # the local (GIN) branch runs beside the global one
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
-        cap = max(plan.edge_capacity, 1)
+        cap = max(plan.work_capacity, 1)  # rows of the per-edge networks: unordered pairs when plan.upairs
         # TS variant (edge_cat): the local edge encoder needs its own d_emb / tmp scratch
         self.local_scratch = ([torch.empty(cap, h, dtype=torch.float32, device=plan.device) for _ in range(2)]
                               if self.ts else [None, None])
@@ -425,11 +425,11 @@ class DualScoreEngine:
     def evaluate(self, pos):
         lib = L.load()
         plan, ws, s = self.plan, self.ws, _stream()
-        b, e = C.byref(plan.c_batch), C.byref(plan.c_edges)
+        b, e = C.byref(plan.c_work_batch), C.byref(plan.c_work_edges)
         d_emb, tmp, ea_g, ea_l, ef0, ef1, efl = ws.edge
         hbuf, nf0, nf1, nf2, hloc, nf0l, nf1l = ws.node
         plan.build_edges(pos, self.cutoff)
-        codes = L.ptr(plan.tab1)
+        codes = L.ptr(plan.work_tab1)
         main = torch.cuda.current_stream()
         # local branch (independent of the global one) on the side stream: edge encoder on all edges,
         # GIN + pair MLP restricted to type > 0 by masks
@@ -458,11 +458,16 @@ class DualScoreEngine:
     def score_channels(self, clip, clip_local, w_global):
         """dualenc.py:827-849: local score on type > 0 edges (+ optional clip_local); global
         score on the remaining edges, clipped, weighted by w_global."""
+        index = self.plan.edge_upair.data_ptr() if self.plan.upairs else None
         ch0 = L.ScoreChannel(self.edge_inv_local.data_ptr(), self.plan.tab0.data_ptr(), 1,
-                             float(clip_local) if clip_local is not None else 0.0, 1.0)
+                             float(clip_local) if clip_local is not None else 0.0, 1.0, index)
         ch1 = L.ScoreChannel(self.edge_inv_global.data_ptr(), self.plan.tab0.data_ptr(), 2,
-                             float(clip) if clip is not None else 0.0, float(w_global))
+                             float(clip) if clip is not None else 0.0, float(w_global), index)
         return ch0, ch1
+
+    def directed(self, per_row, e):
+        """A per-row result of the edge networks for the first e directed edges."""
+        return per_row[self.plan.edge_upair[:e].long()] if self.plan.upairs else per_row[:e]
 
     num_members = 1
 

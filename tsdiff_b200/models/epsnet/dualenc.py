@@ -73,8 +73,8 @@ class DualEncoderEpsNetwork(nn.Module):
         e = plan.edge_count()
         etype = plan.tab0[:e].long()
         local = etype > 0
-        inv_g = eng.edge_inv_global[:e].unsqueeze(-1).clone()
-        inv_l = eng.edge_inv_local[:e][local].unsqueeze(-1)
+        inv_g = eng.directed(eng.edge_inv_global, e).unsqueeze(-1).clone()
+        inv_l = eng.directed(eng.edge_inv_local, e)[local].unsqueeze(-1)
         if not return_edges:
             return inv_g, inv_l
         edge_index = torch.stack([plan.row[:e], plan.col[:e]], dim=0).long()
