@@ -297,6 +297,11 @@ typedef struct {
   int32_t traj_steps;      /* rows of traj */
   int32_t traj_base_step;  /* traj slot = step - traj_base_step (skipped when out of range) */
   int32_t rule;            /* TSD_RULE_LD (0) or TSD_RULE_DDPM (1) */
+  const float* node_score; /* (N,3) or NULL.  When set, the per-atom score eq_transform(edge_inv / inv_div) is NOT
+                            * recomputed from channel 0 but read from here (then clipped with ch0->clip): the
+                            * ensemble-member-per-GPU mode, where every rank runs tsd_eq_transform on its own
+                            * members' edge_inv and the (N,3) partial scores are summed across ranks first
+                            * (eq_transform is linear in edge_inv, sampler.py:96-111,208-209). */
 } tsd_ld_params_t;
 
 int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, float* pos,

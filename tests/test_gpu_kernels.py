@@ -503,3 +503,18 @@ def test_asymmetric_bond_list_disables_pair_sharing(syn4):
     keep[0] = False  # drop one direction of a bond: tables are no longer symmetric
     plan = E.BatchPlan(0, d["batch"], d["bond_index"][:, keep], d["bond_type"][keep], 4, 3, upairs=True)
     assert not plan.upairs and plan.c_work_edges is plan.c_edges
+
+
+def test_member_per_gpu_ensemble():
+    """BASELINE config 3: one ensemble member per GPU, per-step all-reduce of the (N,3) scores; needs 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgpu_ensemble_check.py")
+    port = 29600 + os.getpid() % 300
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), script],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]

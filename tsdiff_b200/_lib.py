@@ -63,7 +63,7 @@ class LdParams(C.Structure):
     _fields_ = [("sched", C.c_void_p), ("num_steps", C.c_int32), ("step_counter", C.c_void_p),
                 ("ticket", C.c_void_p), ("nan_flag", C.c_void_p), ("noise", C.c_void_p), ("seed", C.c_uint64),
                 ("atom_offset", C.c_int64), ("inv_div", C.c_float), ("clip_pos", C.c_float), ("traj", C.c_void_p),
-                ("traj_steps", C.c_int32), ("traj_base_step", C.c_int32), ("rule", C.c_int32)]
+                ("traj_steps", C.c_int32), ("traj_base_step", C.c_int32), ("rule", C.c_int32), ("node_score", C.c_void_p)]
 
 
 RULE_LD, RULE_DDPM = 0, 1

@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
     const float step_size = sc[0], sigma = sc[1], nscale = sc[2];
     const bool use1 = !ddpm && ch1.inv != nullptr && sc[3] != 0.f;
     const int e0 = e.row_ptr[n0], count = e.row_ptr[n0 + n] - e0;  // this graph's edges are contiguous
-    const bool staged = count <= smem_edge_cap;
+    const bool external = ld.node_score != nullptr;  // per-atom scores already reduced over the ensemble ranks
+    const bool staged = !external && count <= smem_edge_cap;
     LdSmem sm;
     sm.term0 = k7_dyn;
     sm.term1 = k7_dyn + 3 * (size_t)smem_edge_cap;
@@ -206,7 +207,9 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
     }
     for (int li = threadIdx.x; li < n; li += blockDim.x) {
       const int i = n0 + li;
-      float3 eps = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, i) : tsd_node_score(ch0, e, spos, n0, i, ld.inv_div);
+      float3 eps;
+      if (external) eps = make_float3(ld.node_score[3 * (size_t)i], ld.node_score[3 * (size_t)i + 1], ld.node_score[3 * (size_t)i + 2]);
+      else eps = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, i) : tsd_node_score(ch0, e, spos, n0, i, ld.inv_div);
       eps = tsd_clip_norm(eps, ch0.clip);
       if (use1) {
         float3 g1 = staged ? k7_node_sum(e, sm.term1, sm.in_local, e0, i) : tsd_node_score(ch1, e, spos, n0, i, ld.inv_div);
@@ -278,8 +281,9 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
 
 extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, float* pos, const tsd_score_channel_t* ch0,
                            const tsd_score_channel_t* ch1, const tsd_ld_params_t* ld, tsd_stream_t stream) {
-  TSD_REQUIRE(batch && edges && pos && ch0 && ch0->inv && ld && ld->sched && ld->step_counter && ld->ticket &&
-              ld->nan_flag);
+  TSD_REQUIRE(batch && edges && pos && ch0 && (ch0->inv || ld->node_score) && ld && ld->sched && ld->step_counter &&
+              ld->ticket && ld->nan_flag);
+  TSD_REQUIRE(!(ld->node_score && ch1 && ch1->inv));  // the reduced-score mode is single channel
   TSD_REQUIRE(batch->max_graph_nodes <= TSD_MAX_GRAPH_NODES);
   TSD_REQUIRE(ld->rule == TSD_RULE_LD || ld->rule == TSD_RULE_DDPM);
   if (batch->num_graphs == 0) return TSD_OK;

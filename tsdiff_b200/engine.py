@@ -478,7 +478,11 @@ class LangevinRunner:
     a device step counter (the score net ignores the time step)."""
 
     def __init__(self, engine, ch0, ch1, sched, pos, noise=None, seed=0, atom_offset=0, clip_pos=None,
-                 keep_traj=True, use_graph=True, rule=L.RULE_LD):
+                 keep_traj=True, use_graph=True, rule=L.RULE_LD, reduce=None, ensemble_size=None):
+        """reduce / ensemble_size: the ensemble-member-per-GPU mode.  `engine` holds this rank's members only;
+        every step the rank's partial per-atom scores eq_transform(sum of local edge_inv / ensemble_size) are
+        summed over the ranks by `reduce(tensor)` (in place, e.g. an NCCL all-reduce) before the update.  All
+        ranks hold the same positions and draw the same noise, so they stay in lockstep without a broadcast."""
         assert sched.size(1) == (8 if rule == L.RULE_DDPM else 4)
         self.engine, self.plan = engine, engine.plan
         dev = self.plan.device
@@ -494,18 +498,32 @@ class LangevinRunner:
         self.traj = (torch.empty(self.n_steps, self.plan.num_nodes, 3, dtype=torch.float32, device=dev)
                      if keep_traj else None)
         self.ch0, self.ch1 = ch0, ch1
+        self.reduce = reduce
+        self.node_eq = None
+        inv_div = float(engine.num_members)
+        if reduce is not None:
+            assert ch1 is None and ensemble_size is not None and ensemble_size >= engine.num_members
+            self.node_eq = torch.zeros(max(self.plan.num_nodes, 1), 3, dtype=torch.float32, device=dev)
+            inv_div = float(ensemble_size)
+        self.inv_div = inv_div
         self.ld = L.LdParams(
             self.sched.data_ptr(), self.n_steps, self.step_counter.data_ptr(), self.ticket.data_ptr(),
             self.nan_flag.data_ptr(), self.noise.data_ptr() if self.noise is not None else None,
-            int(seed) & 0xFFFFFFFFFFFFFFFF, int(atom_offset), float(engine.num_members),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(atom_offset), inv_div,
             float(clip_pos) if clip_pos is not None else 0.0,
-            self.traj.data_ptr() if self.traj is not None else None, self.n_steps if keep_traj else 0, 0, int(rule))
+            self.traj.data_ptr() if self.traj is not None else None, self.n_steps if keep_traj else 0, 0, int(rule),
+            self.node_eq.data_ptr() if self.node_eq is not None else None)
         self.use_graph = use_graph
         self.graph = None
 
     def _one_step(self):
         lib = L.load()
         self.engine.evaluate(self.pos)
+        if self.reduce is not None:
+            L.check(lib.tsd_eq_transform(C.byref(self.plan.c_batch), C.byref(self.plan.c_edges), L.ptr(self.pos),
+                                         C.byref(self.ch0), self.inv_div, L.ptr(self.node_eq), _stream()),
+                    "tsd_eq_transform")
+            self.reduce(self.node_eq)
         L.check(lib.tsd_ld_step(C.byref(self.plan.c_batch), C.byref(self.plan.c_edges), L.ptr(self.pos),
                                 C.byref(self.ch0), C.byref(self.ch1) if self.ch1 is not None else None,
                                 C.byref(self.ld), _stream()), "tsd_ld_step")
@@ -526,7 +544,9 @@ class LangevinRunner:
             self._one_step()
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # with a collective in the step, other threads (the NCCL watchdog) issue CUDA calls during capture
+        mode = dict(capture_error_mode="thread_local") if self.reduce is not None else {}
+        with torch.cuda.graph(self.graph, **mode):
             self._one_step()
         self._reset()
 

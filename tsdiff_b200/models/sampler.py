@@ -45,7 +45,10 @@ class EnsembleSampler(nn.Module):
         (n_steps,N,3) tensor used instead of torch.randn_like; init_noise= (N,3) tensor used
         instead of the torch.randn draw of the from_ts_guess start; seed= Philox seed (default
         torch.initial_seed()); keep_traj=; atom_offset= global index of the first atom of this
-        shard; use_graph=."""
+        shard; use_graph=; ensemble_group= a torch.distributed process group whose ranks each hold a
+        DIFFERENT subset of the ensemble members (`self.models`) and the SAME batch: the per-atom
+        scores are all-reduced every step, which reproduces the reference's per-step mean over all
+        members (sampler.py:96-111) with one member per GPU (BASELINE config 3)."""
         from .. import _lib as L
         sampling_type = kwargs.get("sampling_type", "ddpm")
         if sampling_type not in ("ld", "ddpm"):
@@ -71,7 +74,16 @@ class EnsembleSampler(nn.Module):
         if sampling_type == "ddpm":
             sched, rule = E.ddpm_schedule(self.betas, t_end, n_steps), L.RULE_DDPM
         ch0, ch1 = eng.score_channels(clip)
-        runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, noise=kwargs.get("noise"),
+        reduce, ensemble_size = None, None
+        group = kwargs.get("ensemble_group")
+        if group is not None:
+            import torch.distributed as dist
+            count = torch.tensor([len(self.models)], dtype=torch.int64, device=pos.device)
+            dist.all_reduce(count, group=group)
+            ensemble_size = int(count.item())
+            reduce = lambda t: dist.all_reduce(t, group=group)  # noqa: E731
+        runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, reduce=reduce, ensemble_size=ensemble_size,
+                                  noise=kwargs.get("noise"),
                                   seed=kwargs.get("seed", torch.initial_seed()),
                                   atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
                                   keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True),
