@@ -119,3 +119,34 @@ def test_workspace_bytes_is_host_arithmetic():
         assert eb.value == 28900 * 256 * 4 and nb.value == 1750 * 256 * 4
         assert ne.value == 7 and nn.value == want_nodes
     assert lib.tsd_workspace_bytes(10, 10, 0, 0, 0, None, None, None, None) != 0  # invalid hidden
+
+
+def test_ddpm_schedule_matches_oracle_coefficients():
+    """engine.ddpm_schedule (the 8-column table K7 reads) against the oracle's per-step restatement of
+    sampler.py:216-236, for the default range and for a denoise_from_time_t range that reaches t = 0."""
+    from oracle import tsdiff_oracle as O
+    from tsdiff_b200 import engine as E
+    betas, _ = O.schedule_tensors(TRAIN_CONFIG_MODEL)
+    for t_end, n_steps in ((5000, 7), (12, 12), (600, 3)):
+        table = E.ddpm_schedule(betas, t_end, n_steps)
+        assert table.shape == (n_steps, 8) and table.dtype == torch.float32
+        seq = list(range(t_end - n_steps, t_end))
+        seq_next = [-1] + seq[:-1]
+        for k, (i, j) in enumerate(zip(reversed(seq), reversed(seq_next))):
+            want = torch.cat(O.ddpm_coefficients(betas, i, j))
+            assert torch.equal(table[k], want), (t_end, k)
+    last = E.ddpm_schedule(betas, 12, 12)[-1]  # t = 0: no noise, atm1 = 1
+    assert float(last[6]) == 0.0 and float(last[7]) == 1.0
+
+
+def test_ld_schedule_matches_golden_constants():
+    import json
+    from oracle import tsdiff_oracle as O
+    from tsdiff_b200 import engine as E
+    _, alphas = O.schedule_tensors(TRAIN_CONFIG_MODEL)
+    sched, sigmas = E.ld_schedule(alphas, 5000, 1e-7)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "schedule.json")))
+    assert abs(float(sigmas[0]) - gold["sigma_0"]) < 1e-9 and abs(float(sigmas[-1]) - gold["sigma_last"]) < 1e-6
+    assert sched.shape == (5000, 4) and float(sched[0, 1]) == float(sigmas[-1])  # first step uses sigma_T
+    step = 1e-7 * (float(sigmas[-1]) / 0.01) ** 2
+    assert abs(float(sched[0, 0]) - step) < 1e-6 * step
