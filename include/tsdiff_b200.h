@@ -265,10 +265,14 @@ int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float
  *   LD:   pos = center(pos + step_size[k] * eps / sigma[k] + noise * noise_scale[k])
  *   DDPM: pos_c = c0 pos; pos0 = c1 pos_c - c2 (-eps); mean = (c3 pos0 + c4 pos_c) / c5;
  *         pos = center((mean + c6 noise) / c7)     (channel 0 only; every product / sum rounded)
+ *   DDPM_DUALENC: pos0 = c0 pos - c1 (-eps); pos = center((c2 pos0 + c3 pos) / c4 + c5 noise)
+ *   GENERALIZED:  pos = center(pos - (-eps) c0 + noise c1)
  * noise: external tensor (n_steps, N, 3) if given, else Philox4x32-10 keyed by
  * (seed, step, atom_offset + atom) + Box-Muller.  mask mode: 0 all edges, 1 tab != 0, 2 tab == 0. */
 #define TSD_RULE_LD 0
-#define TSD_RULE_DDPM 1
+#define TSD_RULE_DDPM 1          /* EnsembleSampler `ddpm`, sampler.py:215-236 */
+#define TSD_RULE_DDPM_DUALENC 2  /* dualenc `ddpm_noisy` / `ddpm_det`, dualenc.py:906-944 */
+#define TSD_RULE_GENERALIZED 3   /* dualenc `generalized`, dualenc.py:872-904 */
 
 typedef struct {
   const float* inv;     /* (E) -- or (U) when inv_index is given -- or NULL to disable the channel */
@@ -283,7 +287,10 @@ typedef struct {
   const float* sched;      /* rule LD:   (num_steps, 4): step_size, sigma, noise_scale, use_channel1
                             * rule DDPM: (num_steps, 8): sqrt(at), sqrt(1/at), sqrt(1/at - 1), sqrt(atm1) beta_t,
                             *   sqrt(1 - beta_t) (1 - atm1), 1 - at, mask exp(0.5 log beta_t), sqrt(atm1)
-                            *   (sampler.py:216-236; the caller evaluates them with the reference's fp32 ops) */
+                            *   (sampler.py:216-236; the caller evaluates them with the reference's fp32 ops)
+                            * rule DDPM_DUALENC: (num_steps, 8): sqrt(1/at), sqrt(1/at - 1), sqrt(atm1) beta_t,
+                            *   sqrt(1 - beta_t) (1 - atm1), 1 - at, mask exp(0.5 logvar), use_channel1, 0
+                            * rule GENERALIZED: (num_steps, 4): step_size_pos, step_size_noise, 0, use_channel1 */
   int32_t num_steps;       /* rows of sched / noise; steps beyond it are no-ops */
   int32_t* step_counter;   /* (1) device */
   int32_t* ticket;         /* (1) device scratch, zero-initialised once */
@@ -296,7 +303,7 @@ typedef struct {
   float* traj;             /* (traj_steps, N, 3) or NULL */
   int32_t traj_steps;      /* rows of traj */
   int32_t traj_base_step;  /* traj slot = step - traj_base_step (skipped when out of range) */
-  int32_t rule;            /* TSD_RULE_LD (0) or TSD_RULE_DDPM (1) */
+  int32_t rule;            /* TSD_RULE_* */
   const float* node_score; /* (N,3) or NULL.  When set, the per-atom score eq_transform(edge_inv / inv_div) is NOT
                             * recomputed from channel 0 but read from here (then clipped with ch0->clip): the
                             * ensemble-member-per-GPU mode, where every rank runs tsd_eq_transform on its own

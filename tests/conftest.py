@@ -49,6 +49,20 @@ DDPM_CASES = {
 
 
 @pytest.fixture(scope="session")
+def golden_dualenc_branches():
+    """dualenc.py:861-944 branches (tests/golden/make_golden_dualenc_branches.py)."""
+    return torch.load(os.path.join(GOLDEN, "golden_dualenc_branches.pt"), weights_only=False)
+
+
+DUALENC_BRANCH_CASES = {
+    "a_rxn0_ddpm_noisy10": dict(clip=10.0, clip_local=10.0, sampling_type="ddpm_noisy"),
+    "a_syn4_ddpm_det6": dict(clip=10.0, clip_local=10.0, sampling_type="ddpm_det"),
+    "a_rxn0_generalized8": dict(clip=10.0, clip_local=10.0, sampling_type="generalized", eta=1.0),
+    "a_syn4_generalized6_eta05": dict(clip=10.0, clip_local=10.0, w_global=0.5, sampling_type="generalized", eta=0.5),
+}
+
+
+@pytest.fixture(scope="session")
 def rxn0():
     return torch.load(os.path.join(GOLDEN, "rxn0_graph.pt"), weights_only=False)
 

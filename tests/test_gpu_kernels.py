@@ -15,7 +15,7 @@ from tsdiff_b200 import engine as E
 from tsdiff_b200.config import QM9_DEFAULT_MODEL, TRAIN_CONFIG_MODEL
 from tsdiff_b200.synthetic import make_batch, shard_batch
 
-from conftest import DDPM_CASES, graph_for
+from conftest import DDPM_CASES, DUALENC_BRANCH_CASES, graph_for
 from helpers import make_model, max_rel_err, oracle_params, rel_err, to_dev
 
 pytestmark = pytest.mark.gpu
@@ -518,3 +518,20 @@ def test_member_per_gpu_ensemble():
                           "--master-addr", "127.0.0.1", "--master-port", str(port), script],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("case", sorted(DUALENC_BRANCH_CASES))
+def test_dualenc_sampler_branches_vs_reference_golden(case, golden_dualenc_branches, rxn0, syn4):
+    """DualEncoderEpsNetwork.langevin_dynamics_sample with ddpm_noisy (its default), ddpm_det and generalized
+    (dualenc.py:861-944) against the reference's own trajectories, same injected noise."""
+    g, ref, kw = graph_for(case, rxn0, syn4), golden_dualenc_branches[case], DUALENC_BRANCH_CASES[case]
+    m = make_model("dualenc", 0, DEV)
+    d = to_dev(g, DEV)
+    n_steps = ref["noise"].size(0)
+    pos, traj = m.langevin_dynamics_sample(d["atom_type"], ref["pos_init"].to(DEV), d["bond_index"], d["bond_type"],
+                                           d["batch"], g["num_graphs"], extend_order=True, n_steps=n_steps,
+                                           step_lr=1e-7, noise=ref["noise"], **kw)
+    scale = max(1.0, float(ref["traj"].abs().max()))  # the ddpm branches blow positions up at random init
+    assert len(traj) == n_steps
+    assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4 * scale
+    assert (pos.cpu() - ref["pos"]).abs().max() < 1e-4 * scale

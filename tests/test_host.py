@@ -150,3 +150,23 @@ def test_ld_schedule_matches_golden_constants():
     assert sched.shape == (5000, 4) and float(sched[0, 1]) == float(sigmas[-1])  # first step uses sigma_T
     step = 1e-7 * (float(sigmas[-1]) / 0.01) ** 2
     assert abs(float(sched[0, 0]) - step) < 1e-6 * step
+
+
+def test_dualenc_branch_schedule_matches_oracle_coefficients():
+    """engine.dualenc_branch_schedule against the oracle's restatement of dualenc.py:861-944, including
+    the last time index (t = 0: no noise)."""
+    from oracle import tsdiff_oracle as O
+    from tsdiff_b200 import engine as E
+    betas, alphas = O.schedule_tensors(QM9_DEFAULT_MODEL)
+    T = alphas.numel()
+    for kind, eta in (("ddpm_noisy", 1.0), ("ddpm_det", 1.0), ("generalized", 1.0), ("generalized", 0.5)):
+        n_steps = 6
+        table = E.dualenc_branch_schedule(alphas, betas, n_steps, 1e-7, kind, eta=eta)
+        seq = list(range(T - n_steps, T))
+        seq_next = [-1] + seq[:-1]
+        for k, (i, j) in enumerate(zip(reversed(seq), reversed(seq_next))):
+            want = torch.cat([c.reshape(1) for c in O.dualenc_step_coefficients(alphas, betas, i, j, kind, 1e-7, eta)])
+            assert torch.equal(table[k, :want.numel()], want), (kind, k)
+            assert float(table[k, 6 if kind != "generalized" else 3]) == 1.0  # global channel on (no start sigma)
+    full = E.dualenc_branch_schedule(alphas, betas, T, 1e-7, "ddpm_noisy")
+    assert float(full[-1, 5]) == 0.0  # t == 0

@@ -11,7 +11,7 @@ from oracle import third_party as tp
 from tsdiff_b200.config import QM9_DEFAULT_MODEL, TRAIN_CONFIG_MODEL
 from tsdiff_b200.synthetic import make_batch
 
-from conftest import DDPM_CASES, GOLDEN, graph_for
+from conftest import DDPM_CASES, DUALENC_BRANCH_CASES, GOLDEN, graph_for
 from helpers import make_model, max_rel_err, oracle_params, rel_err
 
 FP32_TOL = 2e-5  # oracle vs reference on CPU: same op graph, only summation-order noise
@@ -185,3 +185,15 @@ def test_radius_cap_rule():
     assert (deg_in[:33] == 32).all()  # 33 kept incl. self, self dropped (self is among the first 33)
     assert (deg_in[33:] == 33).all()  # centre >= 33: the first 33 atoms are 0..32, self not among them
     assert (idx[0][idx[1] == 40] == torch.arange(33)).all()
+
+
+@pytest.mark.parametrize("case", sorted(DUALENC_BRANCH_CASES))
+def test_dualenc_sampler_branches_match_reference(case, golden_dualenc_branches, rxn0, syn4):
+    """dualenc.py:861-944: ddpm_noisy (the class default), ddpm_det, generalized."""
+    g, ref, kw = graph_for(case, rxn0, syn4), golden_dualenc_branches[case], DUALENC_BRANCH_CASES[case]
+    p = oracle_params(make_model("dualenc", 0))
+    pos, traj = O.dualenc_ld_sample(p, QM9_DEFAULT_MODEL, g["atom_type"], ref["pos_init"], g["bond_index"],
+                                    g["bond_type"], g["batch"], ref["noise"].size(0), 1e-7, noise=ref["noise"], **kw)
+    scale = max(1.0, float(ref["traj"].abs().max()))  # the ddpm branches blow positions up at random init
+    assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4 * scale
+    assert (pos - ref["pos"]).abs().max() < 1e-4 * scale

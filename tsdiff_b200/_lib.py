@@ -66,7 +66,7 @@ class LdParams(C.Structure):
                 ("traj_steps", C.c_int32), ("traj_base_step", C.c_int32), ("rule", C.c_int32), ("node_score", C.c_void_p)]
 
 
-RULE_LD, RULE_DDPM = 0, 1
+RULE_LD, RULE_DDPM, RULE_DDPM_DUALENC, RULE_GENERALIZED = 0, 1, 2, 3
 
 
 # symbol -> argtypes; every function returns int (0 = TSD_OK) unless listed in _RESTYPES

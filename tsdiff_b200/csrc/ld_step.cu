@@ -188,10 +188,12 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
   __syncthreads();
   const int step = sstep;
   if (step < ld.num_steps) {
-    const bool ddpm = ld.rule == TSD_RULE_DDPM;
-    const float* sc = ld.sched + (size_t)(ddpm ? 8 : 4) * step;
+    const int rule = ld.rule;
+    const bool wide = rule == TSD_RULE_DDPM || rule == TSD_RULE_DDPM_DUALENC;  // 8-column tables
+    const float* sc = ld.sched + (size_t)(wide ? 8 : 4) * step;
     const float step_size = sc[0], sigma = sc[1], nscale = sc[2];
-    const bool use1 = !ddpm && ch1.inv != nullptr && sc[3] != 0.f;
+    const float use1_flag = rule == TSD_RULE_DDPM ? 0.f : (rule == TSD_RULE_DDPM_DUALENC ? sc[6] : sc[3]);
+    const bool use1 = ch1.inv != nullptr && use1_flag != 0.f;
     const int e0 = e.row_ptr[n0], count = e.row_ptr[n0 + n] - e0;  // this graph's edges are contiguous
     const bool external = ld.node_score != nullptr;  // per-atom scores already reduced over the ensemble ranks
     const bool staged = !external && count <= smem_edge_cap;
@@ -226,7 +228,24 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
         z = tsd_philox_normal3(ld.seed, step, ld.atom_offset + i);
       }
       float nx, ny, nz;
-      if (ddpm) {
+      if (rule == TSD_RULE_DDPM_DUALENC) {
+        // dualenc.py:906-944 (ddpm_noisy / ddpm_det differ only in the noise coefficient)
+        const float ev[3] = {-eps.x, -eps.y, -eps.z}, zv[3] = {z.x, z.y, z.z};
+        float out[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float p = spos[3 * li + d];
+          const float pos0 = __fsub_rn(__fmul_rn(sc[0], p), __fmul_rn(sc[1], ev[d]));
+          const float mean = __fdiv_rn(__fadd_rn(__fmul_rn(sc[2], pos0), __fmul_rn(sc[3], p)), sc[4]);
+          out[d] = __fadd_rn(mean, __fmul_rn(sc[5], zv[d]));
+        }
+        nx = out[0], ny = out[1], nz = out[2];
+      } else if (rule == TSD_RULE_GENERALIZED) {
+        // dualenc.py:904: pos - et * step_size_pos + noise * step_size_noise, et = -eps
+        nx = __fadd_rn(__fsub_rn(spos[3 * li], __fmul_rn(-eps.x, sc[0])), __fmul_rn(z.x, sc[1]));
+        ny = __fadd_rn(__fsub_rn(spos[3 * li + 1], __fmul_rn(-eps.y, sc[0])), __fmul_rn(z.y, sc[1]));
+        nz = __fadd_rn(__fsub_rn(spos[3 * li + 2], __fmul_rn(-eps.z, sc[0])), __fmul_rn(z.z, sc[1]));
+      } else if (rule == TSD_RULE_DDPM) {
         // sampler.py:223-236, one rounded operation per reference tensor op
         const float ev[3] = {-eps.x, -eps.y, -eps.z}, zv[3] = {z.x, z.y, z.z};
         float out[3];
@@ -285,7 +304,7 @@ extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, f
               ld->ticket && ld->nan_flag);
   TSD_REQUIRE(!(ld->node_score && ch1 && ch1->inv));  // the reduced-score mode is single channel
   TSD_REQUIRE(batch->max_graph_nodes <= TSD_MAX_GRAPH_NODES);
-  TSD_REQUIRE(ld->rule == TSD_RULE_LD || ld->rule == TSD_RULE_DDPM);
+  TSD_REQUIRE(ld->rule >= TSD_RULE_LD && ld->rule <= TSD_RULE_GENERALIZED);
   if (batch->num_graphs == 0) return TSD_OK;
   tsd_score_channel_t off;
   memset(&off, 0, sizeof(off));

@@ -483,7 +483,7 @@ class LangevinRunner:
         every step the rank's partial per-atom scores eq_transform(sum of local edge_inv / ensemble_size) are
         summed over the ranks by `reduce(tensor)` (in place, e.g. an NCCL all-reduce) before the update.  All
         ranks hold the same positions and draw the same noise, so they stay in lockstep without a broadcast."""
-        assert sched.size(1) == (8 if rule == L.RULE_DDPM else 4)
+        assert sched.size(1) == (8 if rule in (L.RULE_DDPM, L.RULE_DDPM_DUALENC) else 4)
         self.engine, self.plan = engine, engine.plan
         dev = self.plan.device
         self.n_steps = sched.size(0)
@@ -587,6 +587,45 @@ def ddpm_schedule(betas, t_end, n_steps):
                                (1 - beta_t).sqrt() * (1 - atm1), 1.0 - at, mask * torch.exp(0.5 * beta_t.log()),
                                atm1.sqrt()]))
     return torch.stack(rows).contiguous()
+
+
+def dualenc_branch_schedule(alphas, betas, n_steps, step_lr, sampling_type, eta=1.0, global_start_sigma=float("inf")):
+    """Coefficient table of dualenc.py:861-944 for i = T-1 ... T-n_steps, j = i-1 (-1 below the first index),
+    evaluated with the reference's own fp32 tensor expressions on the CPU.
+    `generalized`: (n_steps, 4) [step_size_pos, step_size_noise, 0, use_global];
+    `ddpm_noisy` / `ddpm_det`: (n_steps, 8) [sqrt(1/at), sqrt(1/at - 1), sqrt(atm1) beta_t,
+    sqrt(1 - beta_t) (1 - atm1), 1 - at, mask exp(0.5 logvar), use_global, 0]."""
+    alphas, betas = alphas.detach().float().cpu(), betas.detach().float().cpu()
+    sigmas = (1.0 - alphas).sqrt() / alphas.sqrt()
+    cum = (1 - torch.cat([torch.zeros(1), betas], dim=0)).cumprod(dim=0)  # compute_alpha, dualenc.py:776-780
+    t_end = alphas.numel()
+    seq = list(range(t_end - n_steps, t_end))
+    seq_next = [-1] + seq[:-1]
+    rows = []
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        t = torch.tensor([i], dtype=torch.long)
+        at = cum.index_select(0, t + 1)
+        at_next = cum.index_select(0, (torch.ones(1) * j).long() + 1)
+        use_global = (sigmas[i] < global_start_sigma).float().reshape(1)
+        if sampling_type == "generalized":
+            c1 = eta * ((1 - at / at_next) * (1 - at_next) / (1 - at)).sqrt()
+            c2 = ((1 - at_next) - c1 ** 2).sqrt()
+            pos_ld = step_lr * (sigmas[i] / 0.01) ** 2 / sigmas[i]
+            pos_gen = 5 * ((1 - at).sqrt() / at.sqrt() - c2 / at_next.sqrt())
+            step_pos = pos_ld if pos_ld < pos_gen else pos_gen
+            noise_ld = torch.sqrt((step_lr * (sigmas[i] / 0.01) ** 2) * 2)
+            noise_gen = 3 * (c1 / at_next.sqrt())
+            step_noise = noise_ld if noise_ld < noise_gen else noise_gen
+            rows.append(torch.cat([step_pos.reshape(1), step_noise.reshape(1), torch.zeros(1), use_global]))
+        else:
+            atm1 = at_next
+            beta_t = 1 - at / atm1
+            mask = 1 - (t == 0).float()
+            logvar = (beta_t * (1 - atm1) / (1 - at)).log() if sampling_type == "ddpm_det" else beta_t.log()
+            rows.append(torch.cat([(1.0 / at).sqrt(), (1.0 / at - 1).sqrt(), atm1.sqrt() * beta_t,
+                                   (1 - beta_t).sqrt() * (1 - atm1), 1.0 - at, mask * torch.exp(0.5 * logvar),
+                                   use_global, torch.zeros(1)]))
+    return torch.stack(rows).contiguous().float()
 
 
 def ld_schedule(alphas, n_steps, step_lr, global_start_sigma=float("inf")):

@@ -88,24 +88,32 @@ class DualEncoderEpsNetwork(nn.Module):
                                  extend_radius=True, n_steps=100, step_lr=0.0000010, clip=1000, clip_local=None,
                                  clip_pos=None, min_sigma=0, is_sidechain=None, global_start_sigma=float("inf"),
                                  w_global=0.2, w_reg=1.0, **kwargs):
-        """dualenc.py:687-967 with sampling_type='ld' (:946-952).  Extra keyword-only knobs that
-        do not exist in the reference: noise= (n_steps,N,3) tensor replacing torch.randn_like,
-        seed= Philox seed, keep_traj=, atom_offset= (global index of this shard's first atom)."""
+        """dualenc.py:687-967: sampling_type 'ld' (:946-952) and 'ddpm_noisy' (the default),
+        'ddpm_det', 'generalized' with eta= (:861-944).  Extra keyword-only knobs that do not exist
+        in the reference: noise= (n_steps,N,3) tensor replacing torch.randn_like, seed= Philox seed,
+        keep_traj=, atom_offset= (global index of this shard's first atom)."""
+        from ... import _lib as L
         sampling_type = kwargs.get("sampling_type", "ddpm_noisy")
-        if sampling_type != "ld":
-            raise NotImplementedError("sampling_type %r: only 'ld' is on the hot path (SURVEY.md 8(f)-3)"
+        if sampling_type not in ("ld", "ddpm_noisy", "ddpm_det", "generalized"):
+            raise NotImplementedError("sampling_type %r (dualenc.py:861-952 has ld, ddpm_noisy, ddpm_det, generalized)"
                                       % (sampling_type,))
         if is_sidechain is not None or not (extend_order and extend_radius):
             raise NotImplementedError("is_sidechain / extend_*=False are outside the LD hot path")
         eng = self._engine(atom_type, bond_index, bond_type, batch)
         eng.refresh_embeddings()
         sched, sigmas = E.ld_schedule(self.alphas, n_steps, step_lr, global_start_sigma)
+        rule = L.RULE_LD
+        if sampling_type != "ld":
+            sched = E.dualenc_branch_schedule(self.alphas, self.betas, n_steps, step_lr, sampling_type,
+                                              eta=kwargs.get("eta", 1.0), global_start_sigma=global_start_sigma)
+            rule = L.RULE_GENERALIZED if sampling_type == "generalized" else L.RULE_DDPM_DUALENC
         pos = (pos_init.detach().to(torch.float32) * sigmas[-1].to(pos_init.device)).contiguous()
         ch0, ch1 = eng.score_channels(clip, clip_local, w_global)
         runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, noise=kwargs.get("noise"),
                                   seed=kwargs.get("seed", torch.initial_seed()),
                                   atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
-                                  keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True))
+                                  keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True),
+                                  rule=rule)
         pos = runner.run()
         traj = list(runner.traj.cpu().unbind(0)) if runner.traj is not None else []
         return pos, traj
