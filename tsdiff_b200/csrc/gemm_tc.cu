@@ -31,8 +31,11 @@ __host__ __device__ constexpr int tc_stages(int) { return 2; }
 // A-producer groups of the computed-operand kernels.  A group strides TC_GROUPS panels, and the
 // parity wait on a stage's `empty` barrier is only unambiguous when the group cannot fall two
 // phases behind, i.e. when TC_GROUPS <= number of stages: 2 stages -> 2 groups of three warps.
-constexpr int TC_GROUP_THREADS = 96;                 // warps 2-4 and 5-7
 constexpr int TC_GROUPS = 2;
+// Two CTA shapes: 256 threads (2 CTAs/SM: for batches with more tiles than SMs) and 512 threads (one
+// CTA per SM: when the tiles do not fill the GPU anyway, 16 warps halve the latency-bound epilogue
+// and 14 producer warps more than halve the time to compute an A panel).
+__host__ __device__ constexpr int tc_group_threads(int nt) { return (nt - 64) / TC_GROUPS; }  // 96 or 224
 
 // A-operand prologue with the fast activations of this arithmetic mode.  A producer thread
 // always serves the same 16 rows (and the same 16-byte column chunk), so the per-row metadata
@@ -89,8 +92,8 @@ __device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, in
   return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);
 }
 
-template <int ACT, int EPI, int AKIND>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int ACT, int EPI, int AKIND, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
     k_gemm_tf32(const GemmArgs p, int tmem_cols, const __grid_constant__ CUtensorMap map_a,
                 const __grid_constant__ CUtensorMap map_w) {
   extern __shared__ uint8_t smem_dyn[];
@@ -99,7 +102,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   __shared__ uint64_t bar_empty[TC_STAGES];
   __shared__ uint64_t bar_accum;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_dot[TC_BM];
+  constexpr int TC_GROUP_THREADS = tc_group_threads(NT);
+  constexpr int NSL = NT / 128;  // column slices of the epilogue (warps per TMEM lane quarter)
+  __shared__ float s_dot[NSL - 1][TC_BM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) TC_STAMP(0);
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter of this warp, column half
   const int row = q * 32 + lane, m = m0 + row;
   const bool live = m < M;
-  const int cols_per_half = N >> 1;
+  const int cols_per_half = N / NSL;
   constexpr int TLD = 36;  // padded row stride (floats) of the transpose tile: conflict-free float4 access
   float* tile = reinterpret_cast<float*>(smem_gen) + warp * (32 * TLD);
   float cscale = 1.f;
@@ -280,10 +285,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     if (tid == 0 && cc < 128) TC_STAMP(18 + (cc >> 5));
   }
   if (EPI == TSD_EPI_DOT) {
-    if (half == 1) s_dot[row] = dot;
+    if (half > 0) s_dot[half - 1][row] = dot;
     __syncthreads();
     if (half == 0 && live) {
-      float r = (dot + s_dot[row]) + (p.b3 ? p.b3[0] : 0.f);
+      float r = dot;
+#pragma unroll
+      for (int h = 0; h < NSL - 1; ++h) r += s_dot[h][row];
+      r += (p.b3 ? p.b3[0] : 0.f);
       p.out_vec[m] = p.accumulate ? p.out_vec[m] + r : r;
     }
   }
@@ -308,20 +316,22 @@ unsigned long long* tc_dbg_buffer() {
   return buf;
 }
 
-template <int ACT, int EPI, int AKIND>
-int tc_launch(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
-              cudaStream_t stream) {
+template <int ACT, int EPI, int AKIND, int NT>
+int tc_launch_nt(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
+                 cudaStream_t stream) {
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI, AKIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI, AKIND, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
+  const size_t tiles = (size_t)(NT / 32) * 32 * 36 * sizeof(float) + 1024;  // epilogue transpose tiles reuse the pipeline
+  if (smem < tiles) smem = tiles;
   GemmArgs g = g0;
   g.dbg = tc_dbg_buffer();
   if (g.dbg) {
     cudaMemsetAsync(g.dbg, 0, 64 * sizeof(unsigned long long), stream);
   }
-  TSD_CUDA(launch_pdl(k_gemm_tf32<ACT, EPI, AKIND>, dim3(tsd_ceil_div(g.M_cap, TC_BM)), dim3(TC_THREADS), smem, stream, g,
+  TSD_CUDA(launch_pdl(k_gemm_tf32<ACT, EPI, AKIND, NT>, dim3(tsd_ceil_div(g.M_cap, TC_BM)), dim3(NT), smem, stream, g,
                       tmem_cols, map_a, map_w));
   TSD_LAUNCH_CHECK();
   if (g.dbg) {
@@ -339,6 +349,22 @@ int tc_launch(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorMap&
     fprintf(stderr, "\n");
   }
   return TSD_OK;
+}
+
+// 512-thread CTAs when the tiles cannot fill the GPU at two per SM anyway (and every epilogue warp still
+// gets a whole 32-column chunk); TSD_GEMM_THREADS=256/512 forces a shape
+template <int ACT, int EPI, int AKIND>
+int tc_launch(const GemmArgs& g, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
+              cudaStream_t stream) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("TSD_GEMM_THREADS");
+    forced = e ? atoi(e) : 0;
+  }
+  const bool wide_ok = g.N >= 128;
+  const bool wide = wide_ok && (forced == 512 || (forced != 256 && tsd_ceil_div(g.M_cap, TC_BM) <= 148));
+  if (wide) return tc_launch_nt<ACT, EPI, AKIND, 512>(g, tmem_cols, smem, map_a, map_w, stream);
+  return tc_launch_nt<ACT, EPI, AKIND, 256>(g, tmem_cols, smem, map_a, map_w, stream);
 }
 
 template <int EPI, int AKIND>
