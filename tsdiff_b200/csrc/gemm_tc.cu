@@ -25,9 +25,9 @@
 namespace {
 using namespace tc;
 
-// 2 stages (~97 KB at N = 256) so TWO CTAs share an SM (2 x 256 TMEM columns) and every tile of a
-// batch-100 step is resident in a single wave
-__host__ __device__ constexpr int tc_stages(int) { return 2; }
+// 256-thread shape: 2 stages (~97 KB at N = 256) so TWO CTAs share an SM (2 x 256 TMEM columns);
+// 512-thread shape (one CTA per SM): 4 stages, so four panels are in flight behind the TMA latency
+__host__ __device__ constexpr int tc_stages(int nt) { return nt == 512 ? 4 : 2; }
 // A-producer groups of the computed-operand kernels.  A group strides TC_GROUPS panels, and the
 // parity wait on a stage's `empty` barrier is only unambiguous when the group cannot fall two
 // phases behind, i.e. when TC_GROUPS <= number of stages: 2 stages -> 2 groups of three warps.
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
     k_gemm_tf32(const GemmArgs p, int tmem_cols, const __grid_constant__ CUtensorMap map_a,
                 const __grid_constant__ CUtensorMap map_w) {
   extern __shared__ uint8_t smem_dyn[];
-  constexpr int TC_STAGES = tc_stages(AKIND);
+  constexpr int TC_STAGES = tc_stages(NT);
   __shared__ uint64_t bar_full[TC_STAGES];
   __shared__ uint64_t bar_empty[TC_STAGES];
   __shared__ uint64_t bar_accum;
@@ -324,6 +324,7 @@ int tc_launch_nt(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorM
     TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI, AKIND, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
+  smem = (size_t)tc_stages(NT) * (TC_A_PANEL_BYTES + (size_t)g0.N * TC_BK * 4) + 1024;
   const size_t tiles = (size_t)(NT / 32) * 32 * 36 * sizeof(float) + 1024;  // epilogue transpose tiles reuse the pipeline
   if (smem < tiles) smem = tiles;
   GemmArgs g = g0;
@@ -399,8 +400,7 @@ int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream) {
     map_a = map_w;  // unused by the kernel
   }
   const int tmem_cols = g.N < 32 ? 32 : g.N;  // power of two >= 32
-  size_t smem = (size_t)tc_stages(g.a_kind) * (TC_A_PANEL_BYTES + (size_t)g.N * TC_BK * 4) + 1024;
-  if (smem < 40 * 1024) smem = 40 * 1024;  // room for the epilogue's transpose tiles (8 x 4.5 KiB)
+  size_t smem = 0;  // sized per CTA shape in tc_launch_nt
 #define TC_GO(EPI, AKIND) return tc_dispatch_act<EPI, AKIND>(g, tmem_cols, smem, map_a, map_w, stream)
   switch (g.a_kind) {
     case TSD_A_PLAIN:
