@@ -13,7 +13,10 @@
  *    legal inside CUDA-graph stream capture (tsd_bond_order_build excepted: it memsets);
  *  - return value: 0 = TSD_OK, otherwise a TSD_ERR_* code (tsd_error_string explains);
  *  - edge counts live on the device (`num_edges`), kernels are launched at capacity and
- *    exit early, so one captured graph serves every step of a sampling run.
+ *    exit early, so one captured graph serves every step of a sampling run;
+ *  - host threads: entry points keep no per-call state except tsd_schnet_encoder's library-owned
+ *    side streams and events (one set per process); its enqueue is serialised internally, so calls
+ *    from several threads / streams are safe, their node-side work shares the side streams.
  */
 #ifndef TSDIFF_B200_H
 #define TSDIFF_B200_H

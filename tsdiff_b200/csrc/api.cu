@@ -39,6 +39,7 @@ int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int
                               cudaStream_t s);
 
 #include <atomic>
+#include <mutex>
 static thread_local int g_last_cuda_error = 0;
 static std::atomic<long long> g_launches{0};
 void tsd_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -404,7 +405,12 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
   // GEMMs (lin2, fused), and a second kernel on side2 computes h_{l+1} = h_l + lin_l(y) and
   // xh_{l+1} = lin1_{l+2}(h_{l+1}) beside agg_{l+1}.  Inside a CUDA-graph capture the event waits
   // become graph edges.
+  // one set of library-owned side streams / events per process: the enqueue of a whole encoder is serialised
+  // (it is host work of ~60 launches); a later call may re-record the events, waits already enqueued keep
+  // the state they captured
   static EncoderFork fk;
+  static std::mutex fk_mutex;
+  std::lock_guard<std::mutex> fk_lock(fk_mutex);
   TSD_TRY(fk.init(num_blocks));
   cudaStream_t side = fk.side, side2 = fk.side2;
   bool split = nf_pool && nf_pool_count >= 2 && num_blocks >= 2;
