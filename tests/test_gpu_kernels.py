@@ -535,3 +535,30 @@ def test_dualenc_sampler_branches_vs_reference_golden(case, golden_dualenc_branc
     assert len(traj) == n_steps
     assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4 * scale
     assert (pos.cpu() - ref["pos"]).abs().max() < 1e-4 * scale
+
+
+def test_rigid_motion_invariance_batch100():
+    """Size-independent property at BASELINE config-2 size: the score network only sees distances and
+    bond orders, so a rigid motion of every reaction (one rotation, per-reaction translations) leaves the
+    edge set and edge_inv unchanged (up to fp32 rounding of the rotated coordinates) and rotates the
+    per-atom score eq_transform(edge_inv)."""
+    g = make_batch(100, seed=4)
+    m = make_model("condensenc", 0, DEV)
+    d = to_dev(g, DEV)
+    torch.manual_seed(21)
+    pos = (g["pos_init"] * 4.0).to(DEV)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, dtype=torch.float64))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    shift = torch.randn(100, 3, dtype=torch.float64)[g["batch"]] * 5.0
+    pos2 = (pos.double().cpu() @ q.T + shift).float().to(DEV)
+    ei1, idx1, ln1 = m(d["atom_type"], d["r_feat"], d["p_feat"], pos, d["bond_index"], d["bond_type"], d["batch"], None)
+    ei2, idx2, ln2 = m(d["atom_type"], d["r_feat"], d["p_feat"], pos2, d["bond_index"], d["bond_type"], d["batch"], None)
+    assert torch.equal(idx1, idx2), "a pair sits within rounding distance of the cutoff: pick another seed"
+    assert rel_err(ln2, ln1) < 1e-5
+    assert rel_err(ei2, ei1) < EPS_TOL and max_rel_err(ei2, ei1) < EPS_TOL
+    n = pos.size(0)
+    s1 = O.eq_transform(ei1.cpu(), pos.cpu(), idx1.cpu(), ln1.cpu())
+    s2 = O.eq_transform(ei2.cpu(), pos2.cpu(), idx2.cpu(), ln2.cpu())
+    assert s1.shape == (n, 3)
+    assert rel_err(s2.double(), s1.double() @ q.T) < 1e-4
