@@ -58,6 +58,18 @@ __device__ __forceinline__ void chain_epilogue(const ChainArgs& p, const ChainSt
   const int row = q * 32 + lane;
   const int cols_per_half = H / (CH_THREADS / 128);
   constexpr int TLD = 36;
+  if (RESID) {
+    // the later chunks' residual rows: pull them into L1 now, their loads are issued only after the
+    // previous chunk's stores (one L2 round trip per chunk otherwise)
+    for (int cc = 32; cc < cols_per_half; cc += 32) {
+      const int c0 = half * cols_per_half + cc;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float* ptr = st.residual + (size_t)min(m0 + q * 32 + i * 4 + (lane >> 3), M - 1) * H + c0 + 4 * (lane & 7);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+      }
+    }
+  }
   for (int cc = 0; cc < cols_per_half; cc += 32) {
     const int c0 = half * cols_per_half + cc;
     // residual rows first: their L2 latency hides behind the TMEM load and the activation
