@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libtsdiff_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "--threads", "0",
 ]
 
 
