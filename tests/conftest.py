@@ -63,6 +63,12 @@ DUALENC_BRANCH_CASES = {
 
 
 @pytest.fixture(scope="session")
+def golden_loss():
+    """get_loss values (tests/golden/make_golden_loss.py)."""
+    return torch.load(os.path.join(GOLDEN, "golden_loss.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
 def rxn0():
     return torch.load(os.path.join(GOLDEN, "rxn0_graph.pt"), weights_only=False)
 

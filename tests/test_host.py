@@ -68,8 +68,11 @@ def test_no_cpu_fallback():
     g = make_batch(1, seed=0)
     with pytest.raises(L.TsdError):
         m(g["atom_type"], g["r_feat"], g["p_feat"], g["pos_init"], g["bond_index"], g["bond_type"], g["batch"], None)
-    with pytest.raises(NotImplementedError):
-        m.get_loss()
+    args = (g["atom_type"], g["r_feat"], g["p_feat"], g["pos_init"], g["bond_index"], g["bond_type"], g["batch"])
+    with pytest.raises(NotImplementedError):  # gradients enabled: the backward kernels are not built
+        m.get_loss(*args)
+    with torch.no_grad(), pytest.raises(L.TsdError):  # forward value needs the CUDA path too
+        m.get_loss(*args)
 
 
 def test_checkpoint_roundtrip_strict():

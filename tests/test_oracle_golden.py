@@ -197,3 +197,19 @@ def test_dualenc_sampler_branches_match_reference(case, golden_dualenc_branches,
     scale = max(1.0, float(ref["traj"].abs().max()))  # the ddpm branches blow positions up at random init
     assert (torch.stack(traj) - ref["traj"]).abs().max() < 1e-4 * scale
     assert (pos - ref["pos"]).abs().max() < 1e-4 * scale
+
+
+@pytest.mark.parametrize("name", ["syn4", "rxn0"])
+def test_losses_match_reference(name, golden_loss, rxn0, syn4):
+    """get_loss of both networks (condensenc.py:267-328, dualenc.py:425-562) with the reference's own draws."""
+    g = graph_for(name, rxn0, syn4)
+    ref = golden_loss["b_" + name]
+    loss = O.condensenc_loss(oracle_params(make_model("condensenc", 0)), TRAIN_CONFIG_MODEL, g["atom_type"], g["r_feat"],
+                             g["p_feat"], ref["pos"], g["bond_index"], g["bond_type"], g["batch"], ref["time_step"],
+                             ref["pos_noise"])
+    assert loss.shape == ref["loss"].shape and rel_err(loss, ref["loss"]) < 1e-4
+    ref = golden_loss["a_" + name]
+    loss, lg, ll = O.dualenc_loss(oracle_params(make_model("dualenc", 0)), QM9_DEFAULT_MODEL, g["atom_type"], ref["pos"],
+                                  g["bond_index"], g["bond_type"], g["batch"], ref["time_step"], ref["pos_noise"])
+    assert rel_err(loss, ref["loss"]) < 1e-4 and rel_err(lg, ref["loss_global"]) < 1e-4
+    assert rel_err(ll, ref["loss_local"]) < 1e-4

@@ -361,6 +361,28 @@ class CondensedScoreEngine:
         return len(self.members)
 
 
+def eq_transform_directed(plan, pos, values):
+    """models/geometry.py:22-30 on the plan's CURRENT directed edge list: `values` (e,) holds one scalar per
+    directed edge in plan order (0 for edges that do not take part).  Returns (N,3).  Deterministic
+    (per-atom sequential sums in edge order, K7's arithmetic)."""
+    e = values.numel()
+    full = torch.zeros(max(plan.edge_capacity, 1), dtype=torch.float32, device=plan.device)
+    full[:e] = values.reshape(-1).to(torch.float32)
+    out = torch.empty(max(plan.num_nodes, 1), 3, dtype=torch.float32, device=plan.device)
+    ch = L.ScoreChannel(full.data_ptr(), None, 0, 0.0, 1.0, None)
+    L.check(L.load().tsd_eq_transform(C.byref(plan.c_batch), C.byref(plan.c_edges), L.ptr(pos.contiguous()),
+                                      C.byref(ch), 1.0, L.ptr(out), _stream()), "tsd_eq_transform")
+    return out[:plan.num_nodes]
+
+
+def require_no_grad(module, what):
+    """The backward kernels are not built: loss values are available for evaluation only."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        raise NotImplementedError(
+            "%s: forward (validation) value only -- call under torch.no_grad(); training needs the backward "
+            "kernels (SURVEY.md section 8(f)-2, not built yet)" % what)
+
+
 def L_act(name):
     from .models.layers import activation_name
     return activation_name(name)

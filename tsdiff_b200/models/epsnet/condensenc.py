@@ -54,9 +54,45 @@ class CondenseEncoderEpsNetwork(nn.Module):
         eng.evaluate(pos)
         return condensed_outputs(eng, return_edges)
 
-    def get_loss(self, *args, **kwargs):
-        raise NotImplementedError(
-            "training (condensenc.py:267-328) needs the backward kernels: SURVEY.md section 8(f)-2, not built yet")
+    def get_loss(self, atom_type, r_feat, p_feat, pos, bond_index, bond_type, batch, num_nodes_per_graph=None,
+                 num_graphs=None, anneal_power=2.0, extend_order=True, extend_radius=True, time_step=None,
+                 pos_noise=None):
+        """condensenc.py:267-328, FORWARD VALUE ONLY (the validation loop of train.py:150-175 runs it
+        under torch.no_grad(); with gradients enabled it raises NotImplementedError: the backward kernels
+        are not built).  Per-atom loss (N,1).  Keyword-only extras: time_step (G,) and pos_noise (N,3)
+        replace the reference's torch.randint / torch.randn draws (:287-295)."""
+        E.require_no_grad(self, "CondenseEncoderEpsNetwork.get_loss")
+        with torch.no_grad():
+            dev = pos.device
+            if num_graphs is None:
+                num_graphs = int(batch.max().item()) + 1
+            if time_step is None:
+                t0, t1 = self.config.get("t0", 0), self.config.get("t1", self.num_timesteps)
+                half_1 = torch.randint(t0, t1, size=(num_graphs // 2 + 1,), device=dev)
+                time_step = torch.cat([half_1, t0 + t1 - 1 - half_1], dim=0)[:num_graphs]
+            if pos_noise is None:
+                pos_noise = torch.randn(size=pos.size(), device=dev)
+            a = self.alphas.to(dev).index_select(0, time_step.to(dev))
+            a_pos = a.index_select(0, batch).unsqueeze(-1)
+            pos_perturbed = (pos + pos_noise.to(dev) * (1.0 - a_pos).sqrt() / a_pos.sqrt()).to(torch.float32).contiguous()
+            edge_inv, edge_index, edge_length = self(atom_type, r_feat, p_feat, pos_perturbed, bond_index, bond_type,
+                                                     batch, time_step)
+            eng = self._engine(atom_type, r_feat, p_feat, bond_index, bond_type, batch)
+            plan = eng.plan
+            e = plan.edge_count()
+            sel = plan.in_b[:e].bool() if eng.two_graphs else torch.ones(e, dtype=torch.bool, device=dev)
+            a_edge = a.index_select(0, batch.index_select(0, edge_index[0])).unsqueeze(-1)
+            d_gt = (pos[edge_index[0]] - pos[edge_index[1]]).norm(dim=-1).unsqueeze(-1)
+            d_target = (d_gt - edge_length) / (1.0 - a_edge).sqrt() * a_edge.sqrt()
+
+            def on_plan_edges(values):  # results live on the pred_edge_order edges: back to plan order
+                full = torch.zeros(e, dtype=torch.float32, device=dev)
+                full[sel] = values.reshape(-1)
+                return full
+
+            node_eq = E.eq_transform_directed(plan, pos_perturbed, on_plan_edges(edge_inv))
+            pos_target = E.eq_transform_directed(plan, pos_perturbed, on_plan_edges(d_target))
+            return torch.sum((node_eq - pos_target) ** 2, dim=-1, keepdim=True)
 
 
 def condensed_outputs(eng, return_edges=True, divide=1):

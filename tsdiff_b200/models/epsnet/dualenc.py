@@ -80,9 +80,53 @@ class DualEncoderEpsNetwork(nn.Module):
         edge_index = torch.stack([plan.row[:e], plan.col[:e]], dim=0).long()
         return inv_g, inv_l, edge_index, etype, plan.length[:e].unsqueeze(-1).clone(), local
 
-    def get_loss(self, *args, **kwargs):
-        raise NotImplementedError(
-            "training (dualenc.py:376-562) needs the backward kernels: SURVEY.md section 8(f)-2, not built yet")
+    def get_loss(self, atom_type, pos, bond_index, bond_type, batch, num_nodes_per_graph=None, num_graphs=None,
+                 anneal_power=2.0, return_unreduced_loss=False, return_unreduced_edge_loss=False, extend_order=True,
+                 extend_radius=True, is_sidechain=None, time_step=None, pos_noise=None):
+        """dualenc.py:376-562 (model_type 'diffusion'), FORWARD VALUE ONLY: raises NotImplementedError when
+        gradients are enabled (the backward kernels are not built).  Returns loss (N,1), or
+        (loss, loss_global, loss_local) with return_unreduced_loss.  Keyword-only extras: time_step (G,)
+        and pos_noise (N,3) replace the reference's draws (:441-451)."""
+        E.require_no_grad(self, "DualEncoderEpsNetwork.get_loss")
+        if is_sidechain is not None or not (extend_order and extend_radius):
+            raise NotImplementedError("is_sidechain / extend_*=False are outside the built path")
+        with torch.no_grad():
+            dev = pos.device
+            if num_graphs is None:
+                num_graphs = int(batch.max().item()) + 1
+            if time_step is None:
+                half = torch.randint(0, self.num_timesteps, size=(num_graphs // 2 + 1,), device=dev)
+                time_step = torch.cat([half, self.num_timesteps - half - 1], dim=0)[:num_graphs]
+            if pos_noise is None:
+                pos_noise = torch.zeros(size=pos.size(), device=dev)
+                pos_noise.normal_()
+            a = self.alphas.to(dev).index_select(0, time_step.to(dev))
+            a_pos = a.index_select(0, batch).unsqueeze(-1)
+            pos_perturbed = (pos + pos_noise.to(dev) * (1.0 - a_pos).sqrt() / a_pos.sqrt()).to(torch.float32).contiguous()
+            inv_g, inv_l, edge_index, _, edge_length, local = self(atom_type, pos_perturbed, bond_index, bond_type, batch,
+                                                                   time_step, return_edges=True)
+            plan = self._engine(atom_type, bond_index, bond_type, batch).plan
+            a_edge = a.index_select(0, batch.index_select(0, edge_index[0])).unsqueeze(-1)
+            d_gt = (pos[edge_index[0]] - pos[edge_index[1]]).norm(dim=-1).unsqueeze(-1)
+            d_target = (d_gt - edge_length) / (1.0 - a_edge).sqrt() * a_edge.sqrt()
+            global_mask = torch.logical_and(torch.logical_or(edge_length <= self.config.cutoff, local.unsqueeze(-1)),
+                                            ~local.unsqueeze(-1))
+            zero = torch.zeros_like(d_target)
+            tgt_g = E.eq_transform_directed(plan, pos_perturbed, torch.where(global_mask, d_target, zero))
+            eq_g = E.eq_transform_directed(plan, pos_perturbed, torch.where(global_mask, inv_g, zero))
+            loss_global = torch.sum((eq_g - tgt_g) ** 2, dim=-1, keepdim=True)
+            loc = local.unsqueeze(-1)
+            inv_l_full = torch.zeros_like(d_target)
+            inv_l_full[local] = inv_l
+            tgt_l = E.eq_transform_directed(plan, pos_perturbed, torch.where(loc, d_target, zero))
+            eq_l = E.eq_transform_directed(plan, pos_perturbed, inv_l_full)
+            loss_local = torch.sum((eq_l - tgt_l) ** 2, dim=-1, keepdim=True)
+            loss = (2 * loss_global + 5 * loss_local) / 7
+            if return_unreduced_edge_loss:
+                return None  # the reference's branch is `pass` (dualenc.py:556-557)
+            if return_unreduced_loss:
+                return loss, loss_global, loss_local
+            return loss
 
     def langevin_dynamics_sample(self, atom_type, pos_init, bond_index, bond_type, batch, num_graphs, extend_order,
                                  extend_radius=True, n_steps=100, step_lr=0.0000010, clip=1000, clip_local=None,
