@@ -145,3 +145,46 @@ def test_dualenc_forward_tf32_batch100():
     for k in (0, 1):  # edge_inv_global, edge_inv_local
         err = rel_err(out["tf32"][k], out["fp32"][k])
         assert 1e-7 < err < 1e-2, (k, err)  # path A at random init: |edge_inv| ~ 1e3, looser stated bound
+
+
+def test_stress_shape_tf32_asymmetric_pairs_and_ld():
+    """BASELINE config-5 shape at reduced count (24 reactions of ~60 atoms, cutoff 15 A): the 32-neighbour cap
+    binds, so many unordered pairs have only ONE directed edge, and N >= 1024 puts the tensor-core chains on
+    the path.  tf32 against the strict fp32 kernels on identical inputs: identical edge sets, eps within the
+    tf32 bound, and a short LD trajectory within 1e-2 A."""
+    from tsdiff_b200.config import AttrDict, TRAIN_CONFIG_MODEL
+    from tsdiff_b200.models.epsnet import get_model
+    from tsdiff_b200.models.sampler import EnsembleSampler
+    from tsdiff_b200.synthetic import make_batch
+    cfg = AttrDict(dict(TRAIN_CONFIG_MODEL))
+    cfg.edge_cutoff = 15.0
+    cfg.encoder = AttrDict(dict(TRAIN_CONFIG_MODEL.encoder))
+    cfg.encoder.cutoff = 15.0
+    torch.manual_seed(0)
+    m = get_model(cfg).to(DEV)
+    g = make_batch(24, seed=8, min_atoms=55, max_atoms=65)
+    d = to_dev(g, DEV)
+    n = g["atom_type"].numel()
+    assert n >= 1024
+    torch.manual_seed(3)
+    pos = (torch.randn(n, 3) * 4.0).to(DEV)
+    outs = {}
+    for math in ("fp32", "tf32"):
+        m.math = math
+        outs[math] = m(d["atom_type"], d["r_feat"], d["p_feat"], pos, d["bond_index"], d["bond_type"], d["batch"], None)
+    idx = outs["fp32"][1]
+    assert torch.equal(idx, outs["tf32"][1])
+    key = set((idx[0] * n + idx[1]).tolist())
+    one_way = sum(1 for r, c in idx.t().tolist() if c * n + r not in key)
+    assert one_way > 0, "expected one-directional edges under the neighbour cap"
+    assert rel_err(outs["tf32"][0], outs["fp32"][0]) < 3e-3
+    noise = torch.randn(6, n, 3, generator=torch.Generator().manual_seed(5))
+    traj = {}
+    for math in ("fp32", "tf32"):
+        m.math = math
+        ens = EnsembleSampler([m])
+        _, t = ens.dynamic_sampling(d["atom_type"], d["r_feat"], d["p_feat"], d["pos_init"], d["bond_index"],
+                                    d["bond_type"], d["batch"], g["num_graphs"], extend_order=True, n_steps=6,
+                                    step_lr=1e-7, clip=1000, sampling_type="ld", noise=noise)
+        traj[math] = torch.stack(t)
+    assert (traj["tf32"] - traj["fp32"]).abs().max() < 1e-2

@@ -213,3 +213,28 @@ def test_losses_match_reference(name, golden_loss, rxn0, syn4):
                                   g["bond_index"], g["bond_type"], g["batch"], ref["time_step"], ref["pos_noise"])
     assert rel_err(loss, ref["loss"]) < 1e-4 and rel_err(lg, ref["loss_global"]) < 1e-4
     assert rel_err(ll, ref["loss_local"]) < 1e-4
+
+
+def test_oracle_autograd_matches_reference_gradients(golden_loss, syn4):
+    """The oracle is functional PyTorch, so its autograd is the checker for the (not yet built) backward
+    kernels: gradients of get_loss(...).mean() (train.py:128-142) against the reference's own autograd."""
+    gold = json.load(open(os.path.join(GOLDEN, "golden_grads.json")))
+    ref = golden_loss["b_syn4"]
+    m = make_model("condensenc", 0)
+    p = {k: v.clone().requires_grad_(v.is_floating_point() and k not in ("betas", "alphas"))
+         for k, v in oracle_params(m).items()}
+    loss = O.condensenc_loss(p, TRAIN_CONFIG_MODEL, syn4["atom_type"], syn4["r_feat"], syn4["p_feat"], ref["pos"],
+                             syn4["bond_index"], syn4["bond_type"], syn4["batch"], ref["time_step"],
+                             ref["pos_noise"]).mean()
+    assert abs(float(loss.detach()) - gold["loss_mean"]) < 1e-4 * gold["loss_mean"]
+    loss.backward()
+    checked = 0
+    for name, want in gold["params"].items():
+        g = p[name].grad
+        assert g is not None, name
+        assert abs(float(g.double().norm()) - want["norm"]) <= 2e-4 * max(want["norm"], 1e-6), name
+        checked += 1
+    assert checked == 80
+    for name, flat in gold["full"].items():
+        want = torch.tensor(flat).reshape(p[name].shape)
+        assert rel_err(p[name].grad, want) < 2e-4, name
