@@ -86,3 +86,42 @@ def test_load_reference_result_pickle():
     assert b.num_graphs == 3 and b.edge_index.size(1) == 78
     fx = torch.load(os.path.join(GOLDEN, "rxn0_graph.pt"), weights_only=False)
     assert torch.equal(samples[0].edge_index, fx["bond_index"])
+
+
+class _StubSampler:
+    """Duck-typed EnsembleSampler: records the dynamic_sampling call and returns a synthetic trajectory."""
+
+    def __init__(self, n_timesteps=5000):
+        self.alphas = torch.linspace(0.999, 0.01, n_timesteps)
+        self.num_timesteps = n_timesteps
+        self.calls = []
+
+    def dynamic_sampling(self, **kw):
+        self.calls.append(kw)
+        n = kw["atom_type"].numel()
+        traj = [torch.full((n, 3), float(k + 1)) for k in range(kw["n_steps"])] if kw.get("keep_traj", True) else []
+        return torch.arange(n * 3, dtype=torch.float32).reshape(n, 3), traj
+
+
+def test_sample_batch_host_logic_from_ts_guess_and_traj_scaling():
+    """sampling.py:171-216 on the host side: the TS-guess start is divided by sqrt(alpha[start_t - 1]), the
+    trajectory is scaled by sqrt(alpha) of the visited time indices (latest first), results split per reaction."""
+    from tsdiff_b200.data import sample_batch
+    _, data = _reactions([10, 12])
+    batch = Batch.from_data_list(data)
+    model = _StubSampler()
+    res = sample_batch(model, batch, n_steps=4, sampling_type="ld", from_ts_guess=True, denoise_from_time_t=3000,
+                       noise_from_time_t=1500, save_traj=True)
+    call = model.calls[0]
+    want_init = batch.pos / model.alphas[1499].sqrt()
+    assert torch.allclose(call["pos_init"], want_init) and call["noise_from_time_t"] == 1500
+    assert call["denoise_from_time_t"] == 3000 and call["extend_order"] is True and call["num_graphs"] == 2
+    scale = model.alphas[3000 - 4:3000].flip(0).sqrt()
+    assert len(res) == 2 and res[0].pos_gen.shape == (4, 10, 3) and res[1].pos_gen.shape == (4, 12, 3)
+    for k in range(4):
+        assert torch.allclose(res[0].pos_gen[k], torch.full((10, 3), float(k + 1)) * scale[k])
+    # without save_traj: final positions split by reaction, default (random normal) start of the right shape
+    res = sample_batch(model, batch, n_steps=3, sampling_type="ld")
+    assert model.calls[1]["pos_init"].shape == (22, 3) and model.calls[1]["keep_traj"] is False
+    assert torch.equal(res[1].pos_gen, torch.arange(66, dtype=torch.float32).reshape(22, 3)[10:])
+    assert [r.smiles for r in res] == ["rxn0", "rxn1"]
