@@ -4,17 +4,21 @@
 //
 //   CTA tile   : 128 rows x N (N = 64 / 128 / 256 = the whole output row, so the epilogue can
 //                fuse bias / activation / cutoff / bond-embedding gate / row-dot), K streamed
-//                in 32-float (128-byte) panels through a 4-stage shared-memory ring
+//                in 32-float (128-byte) panels through a 2- or 4-stage shared-memory ring
+//   CTA shapes : 256 threads, 2 stages, 2 CTAs/SM (more tiles than SMs)  |  512 threads, 4 stages,
+//                one CTA per SM (grids that cannot fill the GPU: latency matters, not occupancy)
 //   warp roles : warp 0  TMA producer  (one lane: cp.async.bulk.tensor of the W panel and, for
 //                         a dense A, of the A panel; SWIZZLE_128B tensor maps write the UMMA
 //                         canonical K-major layout directly; mbarrier complete_tx)
 //                warp 1  MMA issuer    (one lane: 4 x tcgen05.mma M128 x N x K8 per panel,
 //                         tcgen05.commit releases the stage)
-//                warps 4-7 A producers (only when the A operand is COMPUTED by a prologue of
+//                warps 2..  A producers, two groups alternating panels (only when the A operand is
+//                         COMPUTED by a prologue of
 //                         gemm.cuh -- edge MLP layer 0, bond-embedding gating, pair products:
 //                         values are written with the same swizzle, fence.proxy.async, arrive)
-//                all 8 warps epilogue  (tcgen05.ld of their TMEM lane quarter x column half,
-//                         epilogue in registers, float4 stores or row-dot)
+//                all warps epilogue    (tcgen05.ld of their TMEM lane quarter x column slice,
+//                         epilogue in registers, shared-memory transpose, coalesced float4
+//                         stores or row-dot)
 //   pipelines  : full[s]  (TMA bytes + producer arrivals -> MMA), empty[s] (MMA commit ->
 //                producers), accum (last commit -> epilogue)
 #include <stdio.h>
