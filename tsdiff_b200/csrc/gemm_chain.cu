@@ -1,7 +1,7 @@
 // Chained linear layers on the tensor cores: up to three H x H nn.Linear layers applied to a
 // 128-row tile without the intermediates ever leaving the SM.
 //
-//   stage 0 : acc0 = A . W0^T            A, W0 panels by TMA (2-slot ring), tcgen05.mma kind::tf32
+//   stage 0 : acc0 = A . W0^T            A, W0 panels by TMA (3-slot weight ring), tcgen05.mma kind::tf32
 //   epi   0 : x = act0(acc0 + b0)        TMEM -> registers -> TF32-rounded, written in the UMMA
 //                                        K-major SWIZZLE_128B layout into `abuf` (the next A operand)
 //   stage 1 : acc1 = abuf . W1^T         only W1 streams through the ring
