@@ -17,6 +17,44 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_plan_device(fn):
+    """Runs a method with the engine's device current: the library launches on torch's current stream of
+    the CURRENT device and keeps per-process side streams, so a process that also drives another GPU must
+    not call in with that one current.  (One process per GPU is the supported layout)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with torch.cuda.device(self.plan.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
+def require_cuda_inputs(**tensors):
+    for name, t in tensors.items():
+        _require_cuda(t, name)
+
+
+def resolve_seed(seed):
+    """Philox seed of one sampling call.  The reference draws its noise with torch.randn_like
+    (sampler.py:213, dualenc.py:858), which advances torch's global generator: two calls -- two batches,
+    two `--repeat` copies, the retry after a FloatingPointError (sampling.py:171-236) -- never see the
+    same stream.  Without an explicit seed the key is therefore drawn from the global generator per
+    call: reproducible under torch.manual_seed, different for every call."""
+    if seed is None:
+        return int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
+    return int(seed)
+
+
+def _integer_features(t, name):
+    """r_feat / p_feat are one-hot (preprocessing.py:151-164); the embedding kernel reads them as int64."""
+    if t.is_floating_point():
+        if not bool((t == t.round()).all()):
+            raise L.TsdError("%s holds non-integer values: the CUDA node embedding takes one-hot / integer "
+                             "features (int64), it would truncate them" % name)
+    return t.to(torch.long).contiguous()
+
+
 def _require_cuda(t, name):
     if not t.is_cuda:
         raise L.TsdError("%s must be a CUDA tensor: tsdiff_b200 has no CPU path" % name)
@@ -279,6 +317,11 @@ class CondensedScoreEngine:
         for m in self.models:
             if next(m.parameters()).device != batch.device:
                 raise L.TsdError("model parameters and inputs must live on the same CUDA device")
+        if int(cfg.pred_edge_order) > int(cfg.edge_order):
+            # graph b is kept as a mask over graph a's edge list (graph_build.cu): that needs b's local pairs to
+            # be a subset of a's.  The reference rebuilds the graph (condensenc.py:219-237) and has no such limit.
+            raise NotImplementedError("pred_edge_order (%d) > edge_order (%d): the second graph must be a subset "
+                                      "of the first" % (int(cfg.pred_edge_order), int(cfg.edge_order)))
         self.plan = BatchPlan(0, batch, bond_index, bond_type, int(cfg.edge_order), int(cfg.pred_edge_order), upairs=True)
         self.two_graphs = int(cfg.edge_order) != int(cfg.pred_edge_order)
         plan = self.plan
@@ -291,8 +334,8 @@ class CondensedScoreEngine:
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
         self.edge_inv = torch.zeros(max(plan.work_capacity, 1), dtype=torch.float32, device=plan.device)
         atom_type = atom_type.to(torch.long).contiguous()
-        r_feat = r_feat.to(torch.long).contiguous()
-        p_feat = p_feat.to(torch.long).contiguous()
+        r_feat = _integer_features(r_feat, "r_feat")
+        p_feat = _integer_features(p_feat, "p_feat")
         self.members = []
         self.wv = _WeightView(math)
         for m in self.models:
@@ -307,6 +350,7 @@ class CondensedScoreEngine:
             pair = _pair_mlp_struct(m.grad_dist_mlp, self.wv)
             self.members.append({"z": z, "enc": enc, "keep": keep, "blocks": blocks, "pair": pair})
 
+    @_on_plan_device
     def evaluate(self, pos):
         """One ensemble eps-net evaluation at `pos`; fills plan edges and self.edge_inv (sum
         over members, on the edges of graph a; consumers select graph b with plan.in_b)."""
@@ -432,6 +476,7 @@ class DualScoreEngine:
         self.h0_local = torch.empty(n, h, dtype=torch.float32, device=plan.device)
         self.refresh_embeddings()
 
+    @_on_plan_device
     def refresh_embeddings(self):
         """node_emb lookups (weights are constant during sampling).  The global embedding has
         max_norm=10: looked-up rows are renormalised IN PLACE like nn.Embedding does."""
@@ -444,6 +489,7 @@ class DualScoreEngine:
         L.check(lib.tsd_embedding(plan.num_nodes, L.ptr(self.atom_type), L.ptr(wl), wl.size(0), wl.size(1), 0.0,
                                   L.ptr(self.h0_local), _stream()), "tsd_embedding")
 
+    @_on_plan_device
     def evaluate(self, pos):
         lib = L.load()
         plan, ws, s = self.plan, self.ws, _stream()
@@ -556,6 +602,7 @@ class LangevinRunner:
         self.ticket.zero_()
         self.nan_flag.zero_()
 
+    @_on_plan_device
     def prepare(self):
         """Warm up (loads kernels, outside capture) and capture one step."""
         if not self.use_graph or self.graph is not None:
@@ -572,6 +619,7 @@ class LangevinRunner:
             self._one_step()
         self._reset()
 
+    @_on_plan_device
     def run(self, n_steps=None, check_every=0):
         """Advance n_steps (default: all).  Raises FloatingPointError like sampler.py:248-250 /
         dualenc.py:959-961 if a NaN position was produced (checked after the chunk)."""

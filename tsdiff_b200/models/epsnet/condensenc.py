@@ -38,10 +38,12 @@ class CondenseEncoderEpsNetwork(nn.Module):
         self._cache = EngineCache()
 
     def _engine(self, atom_type, r_feat, p_feat, bond_index, bond_type, batch):
-        return self._cache.get(
-            (atom_type, r_feat, p_feat, bond_index, bond_type, batch), (self.math,),
-            lambda: E.CondensedScoreEngine([self], atom_type, r_feat, p_feat, bond_index, bond_type, batch,
-                                           math=self.math))
+        E.require_cuda_inputs(batch=batch, atom_type=atom_type)
+        with torch.cuda.device(batch.device):
+            return self._cache.get(
+                (atom_type, r_feat, p_feat, bond_index, bond_type, batch), (self.math,),
+                lambda: E.CondensedScoreEngine([self], atom_type, r_feat, p_feat, bond_index, bond_type, batch,
+                                               math=self.math), modules=(self,))
 
     @torch.no_grad()
     def forward(self, atom_type, r_feat, p_feat, pos, bond_index, bond_type, batch, time_step=None,

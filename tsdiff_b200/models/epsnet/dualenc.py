@@ -52,9 +52,11 @@ class DualEncoderEpsNetwork(nn.Module):
         self._cache = EngineCache()
 
     def _engine(self, atom_type, bond_index, bond_type, batch):
-        return self._cache.get((atom_type, bond_index, bond_type, batch), (self.math,),
-                               lambda: E.DualScoreEngine(self, atom_type, bond_index, bond_type, batch,
-                                                         math=self.math))
+        E.require_cuda_inputs(batch=batch, atom_type=atom_type)
+        with torch.cuda.device(batch.device):
+            return self._cache.get((atom_type, bond_index, bond_type, batch), (self.math,),
+                                   lambda: E.DualScoreEngine(self, atom_type, bond_index, bond_type, batch,
+                                                             math=self.math), modules=(self,))
 
     @torch.no_grad()
     def forward(self, atom_type, pos, bond_index, bond_type, batch, time_step=None, edge_index=None,
@@ -154,7 +156,7 @@ class DualEncoderEpsNetwork(nn.Module):
         pos = (pos_init.detach().to(torch.float32) * sigmas[-1].to(pos_init.device)).contiguous()
         ch0, ch1 = eng.score_channels(clip, clip_local, w_global)
         runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, noise=kwargs.get("noise"),
-                                  seed=kwargs.get("seed", torch.initial_seed()),
+                                  seed=E.resolve_seed(kwargs.get("seed")),
                                   atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
                                   keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True),
                                   rule=rule)

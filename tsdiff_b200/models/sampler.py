@@ -22,10 +22,12 @@ class EnsembleSampler(nn.Module):
         self._cache = EngineCache()
 
     def _engine(self, atom_type, r_feat, p_feat, bond_index, bond_type, batch):
-        return self._cache.get(
-            (atom_type, r_feat, p_feat, bond_index, bond_type, batch), (self.math, len(self.models)),
-            lambda: E.CondensedScoreEngine(self.models, atom_type, r_feat, p_feat, bond_index, bond_type, batch,
-                                           math=self.math))
+        E.require_cuda_inputs(batch=batch, atom_type=atom_type)
+        with torch.cuda.device(batch.device):
+            return self._cache.get(
+                (atom_type, r_feat, p_feat, bond_index, bond_type, batch), (self.math, len(self.models)),
+                lambda: E.CondensedScoreEngine(self.models, atom_type, r_feat, p_feat, bond_index, bond_type, batch,
+                                               math=self.math), modules=tuple(self.models))
 
     @torch.no_grad()
     def forward(self, atom_type, r_feat, p_feat, pos, bond_index, bond_type, batch, time_step=None,
@@ -43,8 +45,8 @@ class EnsembleSampler(nn.Module):
         Returns (pos on device, list of n_steps CPU (N,3) tensors).  Raises FloatingPointError when
         a NaN position appears.  Keyword-only extras absent from the reference: noise=
         (n_steps,N,3) tensor used instead of torch.randn_like; init_noise= (N,3) tensor used
-        instead of the torch.randn draw of the from_ts_guess start; seed= Philox seed (default
-        torch.initial_seed()); keep_traj=; atom_offset= global index of the first atom of this
+        instead of the torch.randn draw of the from_ts_guess start; seed= Philox seed (default: drawn
+        from torch's global generator on every call, like the reference's randn_like consumes it); keep_traj=; atom_offset= global index of the first atom of this
         shard; use_graph=; ensemble_group= a torch.distributed process group whose ranks each hold a
         DIFFERENT subset of the ensemble members (`self.models`) and the SAME batch: the per-atom
         scores are all-reduced every step, which reproduces the reference's per-step mean over all
@@ -84,7 +86,7 @@ class EnsembleSampler(nn.Module):
             reduce = lambda t: dist.all_reduce(t, group=group)  # noqa: E731
         runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, reduce=reduce, ensemble_size=ensemble_size,
                                   noise=kwargs.get("noise"),
-                                  seed=kwargs.get("seed", torch.initial_seed()),
+                                  seed=E.resolve_seed(kwargs.get("seed")),
                                   atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
                                   keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True),
                                   rule=rule)
