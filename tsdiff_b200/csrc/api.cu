@@ -413,6 +413,72 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
   std::lock_guard<std::mutex> fk_lock(fk_mutex);
   TSD_TRY(fk.init(num_blocks));
   cudaStream_t side = fk.side, side2 = fk.side2;
+  if (tsd_ceil_div(batch->num_nodes, 64) <= 148) {
+    // Few atoms (batch 100: ~1750): the node side of every block is ONE kernel of N/NT small CTAs -- the
+    // aggregation fused in front of the three linears as transposed (swap-AB) tensor-core GEMMs
+    // (node_update.cu).  x1 ping-pongs between nf0 and nf1: a CTA's aggregation gathers x1 rows of atoms
+    // that other CTAs own, so the next block's x1 must not overwrite them.
+    const int tile = tsd_node_tile(batch->num_nodes);
+    float* x1buf[2] = {nf0, nf1};
+    TSD_CUDA(cudaEventRecord(fk.fork, s));
+    TSD_CUDA(cudaStreamWaitEvent(side, fk.fork, 0));
+    NodeArgs na;
+    memset(&na, 0, sizeof(na));
+    na.num_nodes = batch->num_nodes;
+    na.H = H;
+    na.x = h_in;  // x1 of block 0
+    na.num_stages = 1;
+    na.st[0].W = blocks[0].lin1.weight;
+    na.st[0].store = x1buf[0];
+    TSD_TRY(tsd_node_update_tf32(na, tile, side));
+    for (int l = 0; l < num_blocks; ++l) {
+      const tsd_interaction_t& b = blocks[l];
+      float* filt = (l & 1) ? ef0 : ef1;
+      if (l >= 2) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - 2], 0));  // buffer reuse: block l-2 has read it
+      ChainArgs c;
+      memset(&c, 0, sizeof(c));
+      c.M_cap = batch->edge_capacity;
+      c.M_ptr = edges->num_edges;
+      c.H = H;
+      c.A = edge_attr;
+      c.num_stages = 2;
+      c.st[0] = chain_stage(b.nn0, TSD_ACT_SSP);
+      c.st[1] = chain_stage(b.nn2, TSD_ACT_NONE);
+      c.st[1].scale_len = edges->length;
+      c.st[1].cutoff = b.cutoff;
+      c.st[1].smooth = b.smooth;
+      c.st[1].store = filt;
+      TSD_TRY(tsd_chain_tf32(c, s));
+      TSD_CUDA(cudaEventRecord(fk.edge_done[l], s));
+      TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
+      memset(&na, 0, sizeof(na));
+      na.num_nodes = batch->num_nodes;
+      na.H = H;
+      na.in_ptr = edges->in_ptr;
+      na.in_eid = edges->in_eid;
+      na.in_src = edges->in_src;
+      na.x1 = x1buf[l & 1];
+      na.filt = filt;
+      na.st[0].W = b.lin2.weight;
+      na.st[0].bias = b.lin2.bias;
+      na.st[0].act = TSD_ACT_SSP;
+      na.st[1].W = b.lin.weight;
+      na.st[1].bias = b.lin.bias;
+      na.st[1].residual = l == 0 ? h_in : h_out;
+      na.st[1].store = h_out;
+      na.num_stages = 2;
+      if (l + 1 < num_blocks) {
+        na.st[2].W = blocks[l + 1].lin1.weight;
+        na.st[2].store = x1buf[(l + 1) & 1];
+        na.num_stages = 3;
+      }
+      TSD_TRY(tsd_node_update_tf32(na, tile, side));
+      TSD_CUDA(cudaEventRecord(fk.agg_done[l], side));
+    }
+    TSD_CUDA(cudaEventRecord(fk.join, side));
+    TSD_CUDA(cudaStreamWaitEvent(s, fk.join, 0));
+    return TSD_OK;
+  }
   bool split = nf_pool && nf_pool_count >= 2 && num_blocks >= 2;
   for (int l = 0; l + 1 < num_blocks && split; ++l) split = blocks[l].fused_w && blocks[l].fused_b;
   {

@@ -142,6 +142,28 @@ struct ChainArgs {
   unsigned long long* dbg;  // optional CTA-0 timeline (TSD_GEMM_DBG=1)
 };
 
+// node side of an interaction block for few rows: fused aggregation + transposed chained linears (node_update.cu)
+struct NodeStage {
+  const float* W;         // (H, H) row-major, TF32-rounded shadow
+  const float* bias;      // (H) or NULL
+  int act;                // TSD_ACT_SSP or TSD_ACT_NONE
+  const float* residual;  // (N, H) or NULL: added after the activation
+  float* store;           // (N, H) or NULL
+};
+
+struct NodeArgs {
+  int num_nodes, H, num_stages;
+  const float* x;  // dense (N, H) input of stage 0, or NULL -> fused CFConv aggregation of the fields below
+  const int* in_ptr;
+  const int* in_eid;
+  const int* in_src;
+  const float* x1;    // (N, H)
+  const float* filt;  // (rows, H)
+  NodeStage st[3];
+};
+
+int tsd_node_tile(int num_nodes);                                       // node_update.cu: atoms per CTA
+int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream);
 int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream);           // gemm_chain.cu
 int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream);        // dispatch (api.cu)
 int tsd_gemm_ffma(const GemmArgs& g, cudaStream_t stream);             // gemm_ffma.cu
