@@ -42,7 +42,15 @@ def parse_args():
     ap.add_argument("--network", default="condensenc", choices=["condensenc", "dualenc"])
     ap.add_argument("--math", default=os.environ.get("TSDIFF_B200_MATH", "tf32"), choices=["fp32", "tf32"],
                     help="tf32: tcgen05 tensor cores, fp32 accumulate (DESIGN.md section 4 bounds); fp32: FFMA strict parity")
-    ap.add_argument("--ref-ld-steps", type=int, default=8, help="sampler steps per bounded CPU sample")
+    ap.add_argument("--mode", default="shard", choices=["shard", "ensemble"],
+                    help="shard: every rank samples its own batch (no collective; BASELINE config 2 / weak scaling); "
+                         "ensemble: `--members` checkpoints spread over the ranks, ALL ranks sample the same batch and "
+                         "exchange the per-atom scores every step (BASELINE config 3)")
+    ap.add_argument("--members", type=int, default=1, help="ensemble members (seeds of random-init weights)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary measurements (strict fp32 arm + parity_check, 8-member ensemble, stress rooflines)")
+    ap.add_argument("--ref-ld-steps", type=int, default=14, help="sampler steps per window of the bounded CPU sample "
+                    "(three windows: early / mid / late trajectory)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -115,15 +123,15 @@ def build_inputs(args, rank):
     return make_batch(args.batch, seed=1000 + rank)
 
 
-def make_models(args, device):
+def make_models(args, device, seed=0, math=None):
     from tsdiff_b200.config import QM9_DEFAULT_MODEL, TRAIN_CONFIG_MODEL
     from tsdiff_b200.models.epsnet import get_model
     cfg = TRAIN_CONFIG_MODEL if args.network == "condensenc" else QM9_DEFAULT_MODEL
-    torch.manual_seed(0)
+    torch.manual_seed(seed)
     m = get_model(cfg)
     if device is not None:
         m = m.to(device)
-        m.math = args.math
+        m.math = math or args.math
     return m, cfg
 
 
@@ -135,35 +143,59 @@ def ld_kwargs(args):
 
 
 # ----------------------------------------------------------------------------- reference arm
-def oracle_sample_seconds(args, data, n_sampler_steps, repeats):
-    """Times `repeats` bounded samples (the first n_sampler_steps Langevin steps of the real
-    trajectory) of the reference algorithm restated in oracle/ on the host cores."""
+def oracle_window_seconds(args, data, params, cfg, t_end, n_sampler_steps):
+    """Times `n_sampler_steps` Langevin steps of the reference algorithm (oracle port, dense graph rebuild every
+    step) on the host cores, in the window of the trajectory that ENDS at time index t_end: the per-step cost
+    follows the edge count, which grows along the trajectory (at sigma_max most non-bonded pairs are outside the
+    cutoff, at the end every pair is inside), so the sample takes an early, a middle and a late window.  A window
+    starts from Gaussian positions at that window's noise scale sigma(t_end)."""
     from oracle import tsdiff_oracle as O
+    gen = torch.Generator().manual_seed(7 + t_end)
+    noise = torch.randn(n_sampler_steps, data["atom_type"].numel(), 3, generator=gen)
+    sig = O.sigmas_of(params["alphas"])
+    pos0 = data["pos_init"] * sig[t_end - 1]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        if args.network == "condensenc":
+            O.dynamic_sampling([params], cfg, data["atom_type"], data["r_feat"], data["p_feat"], pos0,
+                               data["bond_index"], data["bond_type"], data["batch"], n_sampler_steps, noise=noise,
+                               keep_traj=False, sampling_type="ld", denoise_from_time_t=t_end, **ld_kwargs(args))
+        else:
+            # the dualenc loop has no denoise_from_time_t: its windows all start at sigma_max (dualenc.py:792-795)
+            O.dualenc_ld_sample(dict(params), cfg, data["atom_type"], data["pos_init"], data["bond_index"],
+                                data["bond_type"], data["batch"], n_sampler_steps, noise=noise, keep_traj=False,
+                                **ld_kwargs(args))
+    return time.perf_counter() - t0
+
+
+def oracle_sample(args, data, n_per_window):
+    """Bounded CPU sample: three windows (early / mid / late) of n_per_window sampler steps each.
+    Returns (seconds per sampler step averaged over the windows, description)."""
     m, cfg = make_models(args, None)
     params = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    gen = torch.Generator().manual_seed(7)
-    noise = torch.randn(n_sampler_steps, data["atom_type"].numel(), 3, generator=gen)
-    times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            if args.network == "condensenc":
-                O.dynamic_sampling_ld([params], cfg, data["atom_type"], data["r_feat"], data["p_feat"],
-                                      data["pos_init"], data["bond_index"], data["bond_type"], data["batch"],
-                                      n_sampler_steps, noise=noise, keep_traj=False, **ld_kwargs(args))
-            else:
-                O.dualenc_ld_sample(dict(params), cfg, data["atom_type"], data["pos_init"], data["bond_index"],
-                                    data["bond_type"], data["batch"], n_sampler_steps, noise=noise, keep_traj=False,
-                                    **ld_kwargs(args))
-        times.append(time.perf_counter() - t0)
-    return times
+    total = params["alphas"].numel()
+    windows = [total, total // 2, max(n_per_window, 16)]
+    secs = [oracle_window_seconds(args, data, params, cfg, t, n_per_window) for t in windows]
+    per_step = sum(secs) / (len(windows) * n_per_window)
+    desc = ("3 windows x %d Langevin steps (ending at time index %s: early / mid / late trajectory, %s ms per step) of "
+            "the same batch on the host cores, oracle port of the reference algorithm in fp32 with its dense graph "
+            "rebuild every step; mean cost per step extrapolated linearly to %d steps"
+            % (n_per_window, "/".join(str(t) for t in windows),
+               "/".join("%.0f" % (x / n_per_window * 1e3) for x in secs), args.ld_steps))
+    return per_step, desc
 
 
 def workload_config(args, world):
-    return {"workload": "full %d-step ld sampling, single checkpoint, batch_size %d synthetic Grambow-shape reactions "
-                        "(10-25 atoms) per GPU" % (args.ld_steps, args.batch),
+    if args.mode == "ensemble":
+        sharding = "%d ensemble members over %d GPU(s), same batch on every rank, per-step score exchange" % (
+            args.members, world)
+    else:
+        sharding = "reactions x%d, no collective" % world
+    return {"workload": "full %d-step ld sampling, %s, batch_size %d synthetic Grambow-shape reactions "
+                        "(10-25 atoms) per GPU" % (args.ld_steps, "single checkpoint" if args.members == 1 else
+                                                   "%d-checkpoint ensemble" % args.members, args.batch),
             "network": args.network, "weights": "random-init seed 0", "reactions_per_gpu": args.batch,
-            "ld_steps": args.ld_steps, "math": args.math, "sharding": "reactions x%d, no collective" % world}
+            "ld_steps": args.ld_steps, "members": args.members, "sharding": sharding}
 
 
 def run_reference(args):
@@ -172,18 +204,25 @@ def run_reference(args):
         return
     torch.set_num_threads(os.cpu_count() or 1)
     data = build_inputs(args, 0)
-    n = args.ref_ld_steps
-    times = oracle_sample_seconds(args, data, n, args.warmup + args.steps)[args.warmup:]
-    per_sampler_step = sum(times) / len(times) / n
+    per_steps = []
+    sample = ""
+    # bounded: the whole --steps/--warmup run stays within a few minutes (~0.3 s per sampler step on 16 cores)
+    n_win = max(2, min(args.ref_ld_steps, int(150.0 / ((args.warmup + args.steps) * 3 * 0.3))))
+    for _ in range(args.warmup + args.steps):
+        per_step, sample = oracle_sample(args, data, n_win)
+        per_steps.append(per_step)
+    per_steps = per_steps[args.warmup:] or per_steps
+    per_sampler_step = sum(per_steps) / len(per_steps) * max(args.members, 1)
     traj_seconds = per_sampler_step * args.ld_steps
     value = args.batch / traj_seconds
-    sample = ("first %d of %d Langevin steps per bench step, reference-faithful dense graph build every step; "
-              "extrapolated linearly to the full trajectory" % (n, args.ld_steps))
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": traj_seconds * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(args, 1),
+           "config": workload_config(args, args.gpus), "math": "fp32 (host)",
            "us_per_eps_step": per_sampler_step * 1e6,
+           "per_gpu_value": value,
+           "note": "host cores do not scale with --gpus: `value` is the throughput of this box's CPUs on the reference "
+                   "algorithm whatever the job size; at N GPUs the repo arm samples N x %d reactions" % args.batch,
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                             "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -195,117 +234,242 @@ def flush_l2(buf):
     buf.zero_()
 
 
-def build_runner(args, model, data_dev, keep_traj=True):
+def build_runner(args, models, data_dev, keep_traj=True, math=None, reduce=None, ensemble_size=None):
     """Device-resident sampler state: engine + CUDA-graph runner, inputs already in HBM."""
     from tsdiff_b200 import engine as E
     d = data_dev
+    math = math or args.math
+    models = models if isinstance(models, (list, tuple)) else [models]
+    model = models[0]
     if args.network == "condensenc":
-        eng = E.CondensedScoreEngine([model], d["atom_type"], d["r_feat"], d["p_feat"], d["bond_index"],
-                                     d["bond_type"], d["batch"], math=args.math)
+        eng = E.CondensedScoreEngine(list(models), d["atom_type"], d["r_feat"], d["p_feat"], d["bond_index"],
+                                     d["bond_type"], d["batch"], math=math)
         sched, sigmas = E.ld_schedule(model.alphas, args.ld_steps, 1e-7)
         ch0, ch1 = eng.score_channels(1000)
     else:
-        eng = E.DualScoreEngine(model, d["atom_type"], d["bond_index"], d["bond_type"], d["batch"], math=args.math)
+        eng = E.DualScoreEngine(model, d["atom_type"], d["bond_index"], d["bond_type"], d["batch"], math=math)
         sched, sigmas = E.ld_schedule(model.alphas, args.ld_steps, 1e-7)
         ch0, ch1 = eng.score_channels(10.0, 10.0, 0.2)
     pos = (d["pos_init"] * sigmas[-1].to(d["pos_init"].device)).contiguous()
-    runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, seed=2022, keep_traj=keep_traj)
+    runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, seed=2022, keep_traj=keep_traj, reduce=reduce,
+                              ensemble_size=ensemble_size)
     return eng, runner
 
 
-def api_call(args, model, data_host, device):
+def api_call(args, models, data_host, device, group=None):
     """The call a user makes (sampling.py:169-209): host tensors -> device, dynamic_sampling /
     langevin_dynamics_sample, trajectory + final positions back on the host."""
     from tsdiff_b200.models.sampler import EnsembleSampler
     d = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in data_host.items()}
     if args.network == "condensenc":
-        ens = EnsembleSampler([model])
+        ens = EnsembleSampler(list(models))
+        extra = {"ensemble_group": group} if group is not None else {}
         pos, traj = ens.dynamic_sampling(d["atom_type"], d["r_feat"], d["p_feat"], d["pos_init"], d["bond_index"],
                                          d["bond_type"], d["batch"], data_host["num_graphs"], extend_order=True,
-                                         n_steps=args.ld_steps, sampling_type="ld", seed=2022, **ld_kwargs(args))
+                                         n_steps=args.ld_steps, sampling_type="ld", seed=2022, **extra, **ld_kwargs(args))
     else:
-        pos, traj = model.langevin_dynamics_sample(d["atom_type"], d["pos_init"], d["bond_index"], d["bond_type"],
-                                                   d["batch"], data_host["num_graphs"], extend_order=True,
-                                                   n_steps=args.ld_steps, sampling_type="ld", seed=2022,
-                                                   **ld_kwargs(args))
+        pos, traj = models[0].langevin_dynamics_sample(d["atom_type"], d["pos_init"], d["bond_index"], d["bond_type"],
+                                                       d["batch"], data_host["num_graphs"], extend_order=True,
+                                                       n_steps=args.ld_steps, sampling_type="ld", seed=2022,
+                                                       **ld_kwargs(args))
     return pos.cpu(), traj
 
 
 def committed_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the top kernels, from
-    the committed `ncu --set full` capture (profiles/r1_ncu_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    return json.load(open(path)) if os.path.exists(path) else {}
+    the committed `ncu --set full` captures (profiles/r2_ncu_traffic.json, else round 1's)."""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            return json.load(open(path))
+    return {}
+
+
+class L2Flush:
+    """Write pass + read pass over more than the 126 MB L2: the read pass evicts the dirty lines of the
+    write pass, so their write-back does not compete with the timed kernel."""
+
+    def __init__(self, device):
+        self.w = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+        self.r = torch.zeros(64 << 20, dtype=torch.float32, device=device)
+
+    def __call__(self):
+        self.w.zero_()
+        self.r.sum()
+
+
+def timed_cold(fn, flush, reps=10, warm=3):
+    """Mean seconds of `fn` alone on the current stream, L2 flushed before every timed call (CUDA events)."""
+    ts = []
+    for _ in range(warm):
+        fn()
+    for _ in range(reps):
+        flush()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        fn()
+        t1.record()
+        torch.cuda.synchronize()
+        ts.append(t0.elapsed_time(t1) * 1e-3)
+    return sum(ts) / len(ts)
 
 
 def kernel_rooflines(args, eng, peaks, device):
     """Live CUDA-event timing (kernel alone, L2 flushed) of the two kernels that matter, on the
     engine's current late-trajectory edge list:
       * the dominant kernel: the fused filter network of one CFConv layer (two chained
-        E x H x H tensor-core GEMMs; the same kernel also runs the node update) -> tensor roofline
-      * the CFConv segmented aggregation (the HBM-bound message-passing kernel) -> HBM roofline."""
+        E x H x H tensor-core GEMMs) -> tensor roofline, against the TF32 peak (= half the measured bf16 peak)
+      * the CFConv segmented aggregation (the message-passing gather) -> HBM roofline."""
     from tsdiff_b200 import _lib as L
     lib = L.load()
     plan, h = eng.plan, eng.hidden
     e = plan.work_count()  # rows of the per-edge kernels: unordered pairs (path B) or directed edges
     e_dir = plan.edge_count()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    # L2 flush = write pass + read pass over 256 MiB each: the read pass evicts the dirty lines of
-    # the write pass, so their write-back does not compete with the timed kernel
-    flush_w = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    flush_r = torch.zeros(64 << 20, dtype=torch.float32, device=device)
+    flush = L2Flush(device)
     ws = eng.ws
     x = ws.edge[2]  # edge_attr of the last evaluation (E_cap, H)
     tmp, out = ws.edge[4], ws.edge[5]
     blocks = eng.members[0]["blocks"] if hasattr(eng, "members") else eng.blocks
     math = L.MATH[args.math]
     traffic = committed_traffic()
-
-    def timed(fn, reps=10):
-        ts = []
-        for _ in range(3):
-            fn()
-        for _ in range(reps):
-            flush_w.zero_()
-            flush_r.sum()
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            fn()
-            t1.record()
-            torch.cuda.synchronize()
-            ts.append(t0.elapsed_time(t1) * 1e-3)
-        return sum(ts) / len(ts)
-
-    t_f = timed(lambda: L.check(lib.tsd_filter_network(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), L.ptr(x),
-                                                       C.byref(blocks[0]), L.ptr(tmp), L.ptr(out), math, stream),
-                                "tsd_filter_network"))
-    # algorithmic = what the reference computes for this launch: two E x H x H layers over the DIRECTED edges
-    # (SURVEY.md 8d); executed = the same over the unordered pairs (both directions share one row)
-    flops = 2 * 2.0 * e_dir * h * h
+    t_f = timed_cold(lambda: L.check(lib.tsd_filter_network(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), L.ptr(x),
+                                                            C.byref(blocks[0]), L.ptr(tmp), L.ptr(out), math, stream),
+                                     "tsd_filter_network"), flush)
+    # executed = what the kernel computes: two rows x H x H layers, one row per unordered pair (both directions of an
+    # edge are bit-identical); reference-equivalent = the same over the DIRECTED edges (SURVEY.md 8d)
     executed = 2 * 2.0 * e * h * h
-    kname = "k_chain_tf32" if args.math == "tf32" else "k_gemm_ffma"
-    tensor = {"bound": "tensor", "kernel": "%s: CFConv filter network nn2(ssp(nn0(edge_attr)))*C, 2 x (E x %d x %d), %s"
+    equivalent = 2 * 2.0 * e_dir * h * h
+    tf32 = args.math == "tf32"
+    peak = peaks["tensor_burst"] / 2 if tf32 else 75.0
+    kname = "k_chain_tf32" if tf32 else "k_gemm_ffma"
+    tensor = {"bound": "tensor", "kernel": "%s: CFConv filter network nn2(ssp(nn0(edge_attr)))*C, 2 x (rows x %d x %d), %s"
                                            % (kname, h, h, args.math),
-              "achieved": flops / t_f / 1e12, "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
-              "frac": flops / t_f / 1e12 / peaks["tensor_burst"], "traffic": traffic.get(kname),
-              "peak_source": peaks["source"] + " bf16 burst (tf32 tensor peak is half of it)",
-              "us_per_launch": t_f * 1e6, "rows": e, "algorithmic_flops": flops, "executed_flops": executed,
-              "executed_tflops": executed / t_f / 1e12,
-              "note": "achieved = reference-equivalent flops (directed edges) / time; the kernel executes them once per "
-                      "unordered pair" if e != e_dir else "no dedup",
-              "algorithmic_bytes": 2 * e_dir * h * 4 + 2 * h * h * 4}
+              "achieved": executed / t_f / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": executed / t_f / 1e12 / peak,
+              "traffic": traffic.get(kname),
+              "peak_source": (peaks["source"] + " bf16 burst / 2 = TF32 dense peak (kind::tf32 runs at half the bf16 rate)")
+              if tf32 else "FP32 FFMA class peak, ~75 TFLOP/s (B200_PROFILING.md fallback)",
+              "definition": "achieved = EXECUTED flops / time (one row per unordered pair)",
+              "us_per_launch": t_f * 1e6, "rows": e, "executed_flops": executed,
+              "reference_equivalent_flops": equivalent, "reference_equivalent_tflops": equivalent / t_f / 1e12,
+              "algorithmic_bytes": 2 * e * h * 4 + 2 * h * h * 4}
     x1 = ws.node[1]
     agg = ws.node[2]
-    t_agg = timed(lambda: L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), h, L.ptr(x1),
-                                                           L.ptr(out), L.ptr(agg), stream), "tsd_cfconv_aggregate"))
+    t_agg = timed_cold(lambda: L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), h,
+                                                                L.ptr(x1), L.ptr(out), L.ptr(agg), stream),
+                                       "tsd_cfconv_aggregate"), flush)
     n = plan.num_nodes
     # algorithmic (SURVEY.md 8d): one filter row per directed edge + x1 once + output + CSR; with pair sharing
     # the filter rows live in a half-size buffer, so the DRAM traffic is lower than that
     nbytes = e_dir * h * 4 + 2 * n * h * 4 + e_dir * 8 + (n + 1) * 4
-    hbm = {"bound": "hbm", "kernel": "k_cfconv_aggregate", "achieved": nbytes / t_agg / 1e9, "peak": peaks["hbm"],
+    hbm = {"bound": "hbm", "kernel": "k_cfconv_aggregate (standalone; inside the step the aggregation is fused into "
+                                     "k_node_update)", "achieved": nbytes / t_agg / 1e9, "peak": peaks["hbm"],
            "unit": "GB/s", "frac": nbytes / t_agg / 1e9 / peaks["hbm"], "traffic": traffic.get("k_cfconv_aggregate"),
-           "peak_source": peaks["source"], "us_per_launch": t_agg * 1e6, "algorithmic_bytes": nbytes}
+           "peak_source": peaks["source"], "us_per_launch": t_agg * 1e6, "algorithmic_bytes": nbytes,
+           "regime": "batch 100: 34 MB per launch, L2 resident inside the step -- latency bound, not HBM bound; the "
+                     "HBM-bound regime is roofline_stress"}
     return tensor, hbm
+
+
+def stress_rooflines(args, peaks, device):
+    """BASELINE config 5 (stress: batch 1000 synthetic reactions of ~60 atoms, cutoff enlarged to 15 A -- the
+    32-neighbour cap binds): K2 (edge build), one CFConv aggregation and one full Langevin step (K2 + eps-net + K7),
+    CUDA-event timed with the L2 flushed, against the measured HBM bandwidth with SURVEY.md 8(d)'s algorithmic bytes."""
+    from tsdiff_b200 import _lib as L
+    from tsdiff_b200 import engine as E
+    from tsdiff_b200.config import AttrDict, TRAIN_CONFIG_MODEL
+    from tsdiff_b200.models.epsnet import get_model
+    from tsdiff_b200.synthetic import make_batch
+    lib = L.load()
+    cfg = AttrDict(dict(TRAIN_CONFIG_MODEL))
+    cfg.edge_cutoff = 15.0
+    cfg.encoder = AttrDict(dict(TRAIN_CONFIG_MODEL.encoder))
+    cfg.encoder.cutoff = 15.0
+    torch.manual_seed(0)
+    model = get_model(cfg).to(device)
+    model.math = args.math
+    g = make_batch(1000, seed=5, min_atoms=55, max_atoms=65)
+    d = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in g.items()}
+    eng = E.CondensedScoreEngine([model], d["atom_type"], d["r_feat"], d["p_feat"], d["bond_index"], d["bond_type"],
+                                 d["batch"], math=args.math)
+    plan, h = eng.plan, eng.hidden
+    sched, _ = E.ld_schedule(model.alphas, 4, 1e-7)
+    pos = (d["pos_init"] * 4.0).contiguous()
+    ch0, ch1 = eng.score_channels(1000)
+    runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, seed=1, keep_traj=False, use_graph=False)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flush = L2Flush(device)
+    eng.evaluate(pos)
+    torch.cuda.synchronize()
+    n, e_dir, rows = plan.num_nodes, plan.edge_count(), plan.work_count()
+    t_k2 = timed_cold(lambda: plan.build_edges(pos, eng.cutoff), flush, reps=5, warm=2)
+    k2_bytes = n * 12 + e_dir * 32  # SURVEY.md 8(d): positions read, 32 B of edge records written per edge
+    ws = eng.ws
+    x1, agg, filt = ws.node[1], ws.node[2], ws.edge[5]
+    t_agg = timed_cold(lambda: L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), h,
+                                                                L.ptr(x1), L.ptr(filt), L.ptr(agg), stream),
+                                       "tsd_cfconv_aggregate"), flush, reps=5, warm=2)
+    agg_bytes = e_dir * h * 4 + 2 * n * h * 4 + e_dir * 8 + (n + 1) * 4
+
+    def one_step():
+        runner.step_counter.zero_()
+        runner._one_step()
+    t_step = timed_cold(one_step, flush, reps=3, warm=1)
+    flops = 3.65e6 * e_dir  # SURVEY.md 8(d): ~3.65 MFLOP per directed edge (condensenc, H = 256, L = 7)
+    return {"workload": "BASELINE config 5: batch 1000 x 55-65 atoms (N = %d), cutoff 15 A, neighbour cap 32 binding: "
+                        "E = %d directed edges, %d network rows" % (n, e_dir, rows),
+            "math": args.math,
+            "edge_build": {"kernel": "k_edge_count + k_edge_emit (K2)", "us": t_k2 * 1e6, "algorithmic_bytes": k2_bytes,
+                           "achieved_gbs": k2_bytes / t_k2 / 1e9, "frac_of_hbm": k2_bytes / t_k2 / 1e9 / peaks["hbm"],
+                           "note": "per-reaction all-pairs tiles in shared memory: latency / shared-memory bound, "
+                                   "its HBM traffic is tiny"},
+            "aggregate": {"kernel": "k_cfconv_aggregate_staged", "bound": "hbm", "us": t_agg * 1e6,
+                          "algorithmic_bytes": agg_bytes, "achieved": agg_bytes / t_agg / 1e9, "peak": peaks["hbm"],
+                          "unit": "GB/s", "frac": agg_bytes / t_agg / 1e9 / peaks["hbm"]},
+            "full_step": {"what": "K2 + eps-net + K7, eager launches", "ms": t_step * 1e3,
+                          "reference_equivalent_tflops": flops / t_step / 1e12, "samples_per_s_at_5000_steps": 1000 / (t_step * 5000)}}
+
+
+def measure_ensemble(args, rank, world, device, group, flush_buf, members=8):
+    """BASELINE config 3: a `members`-checkpoint ensemble (seeds 0..members-1 of random-init weights), member m on
+    rank m % world, every rank sampling the SAME batch; the per-atom scores are exchanged every step so that the
+    reference's per-step mean over all members (sampler.py:96-111) is reproduced.  One full trajectory, device
+    time, max over ranks.  world = 1: all members one after another on one GPU."""
+    import torch.distributed as dist
+    data = build_inputs(args, 0)
+    data_dev = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
+    seeds = [m for m in range(members) if m % world == rank]
+    models = [make_models(args, device, seed=sd)[0] for sd in seeds]
+    reduce = (lambda t: dist.all_reduce(t, group=group)) if world > 1 else None  # noqa: E731
+    eng, runner = build_runner(args, models, data_dev, keep_traj=False, reduce=reduce,
+                               ensemble_size=members if world > 1 else None)
+    runner.prepare()
+    runner.run(n_steps=20)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([full_trajectory(runner, flush_buf)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = float(t.item())
+    checksum = float(runner.pos.double().abs().sum())
+    del runner, eng  # a captured graph with NCCL nodes must be released before the process group goes away
+    return {"value": args.batch / t, "unit": UNIT, "members": members, "members_per_gpu": len(seeds), "n_gpus": world,
+            "us_per_sampler_step": t * 1e6 / args.ld_steps, "trajectories": 1, "ld_steps": args.ld_steps,
+            "exchange": "none (one GPU)" if world == 1 else "NCCL all-reduce of the (N,3) partial scores, captured in the step graph",
+            "final_pos_abs_sum": checksum}
+
+
+def full_trajectory(runner, flush_buf):
+    """One full trajectory from the initial positions; returns device seconds (CUDA events)."""
+    runner._reset()
+    flush_l2(flush_buf)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    runner.run()
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) * 1e-3
 
 
 def run_ours(args):
@@ -315,18 +479,32 @@ def run_ours(args):
                          "host-core baseline)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
     from tsdiff_b200 import _lib as L
     lib = L.load()
     peaks = measured_peaks()
-    data = build_inputs(args, rank)
-    model, cfg = make_models(args, device)
+    ensemble_mode = args.mode == "ensemble"
+    if ensemble_mode:
+        if args.network != "condensenc":
+            raise SystemExit("--mode ensemble is EnsembleSampler's (condensenc) mode")
+        if args.members < world:
+            args.members = 8 if world <= 8 else world
+    data = build_inputs(args, 0 if ensemble_mode else rank)
+    # ensemble mode: member m lives on rank m % world; shard mode: every rank holds all members
+    seeds = [m for m in range(args.members) if (m % world == rank or not ensemble_mode)]
+    models = [make_models(args, device, seed=sd)[0] for sd in seeds]
     data_dev = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
 
     # ---- device-resident throughput: inputs in HBM, one replayed CUDA graph per Langevin step
-    eng, runner = build_runner(args, model, data_dev)
+    reduce = None
+    if ensemble_mode and world > 1:
+        import torch.distributed as dist
+        reduce = lambda t: dist.all_reduce(t, group=group)  # noqa: E731
+    eng, runner = build_runner(args, models, data_dev, reduce=reduce, ensemble_size=args.members if reduce else None)
     c0 = lib.tsd_launch_count()
     runner.use_graph, saved = False, runner.use_graph
     runner._one_step()  # eager step: counts our kernel launches per Langevin step
@@ -344,87 +522,117 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def one_trajectory():
-        runner._reset()
-        flush_l2(flush)
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        runner.run()
-        t1.record()
-        torch.cuda.synchronize()
-        return t0.elapsed_time(t1) * 1e-3
-
     for _ in range(args.warmup):
-        one_trajectory()
+        full_trajectory(runner, flush)
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
-    times = [one_trajectory() for _ in range(args.steps)]
+    times = [full_trajectory(runner, flush) for _ in range(args.steps)]
     barrier()
     clock_info = clocks.stop()
+    pos_final = runner.pos.clone()  # end of the last timed trajectory (Philox seed 2022): parity_check below
     elapsed = torch.tensor([sum(times)], dtype=torch.float64, device=device)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
     elapsed = float(elapsed.item())
-    mean_edges = None
-    value = world * args.batch * args.steps / elapsed
+    job_reactions = args.batch if ensemble_mode else world * args.batch
+    value = job_reactions * args.steps / elapsed
 
     # ---- end to end through the public API: host inputs in, trajectory + positions out
     e2e = None
     if not args.no_e2e:
         pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
         h2d = sum(v.numel() * v.element_size() for v in pinned.values() if torch.is_tensor(v))
-        api_call(args, model, pinned, device)  # warm-up (untimed)
+        api_group = group if (ensemble_mode and world > 1) else None
+        api_call(args, models, pinned, device, api_group)  # warm-up (untimed)
         iters = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
         for _ in range(iters):
-            pos_host, traj = api_call(args, model, pinned, device)
+            pos_host, traj = api_call(args, models, pinned, device, api_group)
         torch.cuda.synchronize()
         t_api = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(t_api, op=dist.ReduceOp.MAX)
         d2h = pos_host.numel() * 4 + sum(t.numel() * 4 for t in traj)
-        e2e = {"value": world * args.batch * iters / float(t_api.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        e2e = {"value": job_reactions * iters / float(t_api.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "iters": iters,
                "includes": "H2D inputs, bond-order tables, graph capture, %d LD steps, D2H trajectory+positions"
                            % args.ld_steps}
 
+    ens_extra = None
+    if world > 1 and not ensemble_mode and args.members == 1 and args.network == "condensenc" and not args.no_extras:
+        # BASELINE config 3 inside the driver's scaling run: 8 members, one (or 8 / N) per GPU, same batch
+        ens_extra = measure_ensemble(args, rank, world, device, group, flush)
     if rank != 0:
         return
-    # ---- per-kernel rooflines (live, rank 0) and the CPU baseline (N = 1 only)
+    # ---- per-kernel rooflines (live, rank 0), secondary arms and the CPU baseline (N = 1 only)
     runner._reset()
     runner.run(n_steps=min(args.ld_steps, 2000))  # a late-trajectory edge list (every pair inside the cutoff)
     mean_edges = eng.plan.edge_count()
+    work_rows = eng.plan.work_count()
     tensor_roof, hbm_roof = kernel_rooflines(args, eng, peaks, device)
+    extras = {}
+    plain = world == 1 and not ensemble_mode and args.members == 1 and not args.no_extras
+    if plain and args.network == "condensenc" and args.math == "tf32":
+        # strict fp32 (FFMA) mode -- the only mode that meets north_star's 1e-4 per-step bound -- on the same
+        # workload, one full trajectory; its final geometries pin the benchmarked tf32 arithmetic (parity_check)
+        m32 = make_models(args, device, seed=0, math="fp32")[0]
+        a32 = argparse.Namespace(**dict(vars(args), math="fp32"))
+        eng32, run32 = build_runner(a32, [m32], data_dev, keep_traj=False, math="fp32")
+        run32.prepare()
+        run32.run(n_steps=20)
+        t32 = full_trajectory(run32, flush)
+        diff2 = ((pos_final - run32.pos) ** 2).sum(1).cpu()
+        rmsd = (torch.zeros(data["num_graphs"]).index_add_(0, data["batch"], diff2) / data["num_nodes_per_graph"]).sqrt()
+        run32._reset()
+        run32.run(n_steps=min(args.ld_steps, 2000))
+        roof32, _ = kernel_rooflines(a32, eng32, peaks, device)
+        extras["strict_fp32"] = {"value": args.batch / t32, "unit": UNIT, "us_per_eps_step": t32 * 1e6 / args.ld_steps,
+                                 "trajectories": 1, "ld_steps": args.ld_steps, "dtype": "f32",
+                                 "bound": "eps <= 1e-4 relative per step (tests/test_gpu_kernels.py)", "roofline": roof32}
+        extras["parity_check"] = {"what": "per-reaction RMSD of the final geometries after %d LD steps, tf32 (the timed "
+                                          "arithmetic) vs the strict fp32 path, same Philox noise (seed 2022), A"
+                                          % args.ld_steps,
+                                  "rmsd_mean": float(rmsd.mean()), "rmsd_max": float(rmsd.max()), "bound": 2e-2,
+                                  "within_bound": bool(float(rmsd.max()) < 2e-2)}
+        del eng32, run32
+    if plain and args.network == "condensenc":
+        # BASELINE config 3 at N = 1: an 8-checkpoint ensemble on one GPU (members evaluated one after another,
+        # edge_inv averaged every step, sampler.py:96-111)
+        extras["ensemble8"] = measure_ensemble(args, 0, 1, device, None, flush)
+        torch.cuda.empty_cache()
+        extras["roofline_stress"] = stress_rooflines(args, peaks, device)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        t_probe = oracle_sample_seconds(args, data, 1, 1)[0]
-        n = int(max(2, min(40, args.cpu_seconds / max(t_probe, 1e-3))))
-        t_sample = oracle_sample_seconds(args, data, n, 1)[0]
-        per_step = t_sample / n
+        n = max(2, min(args.ref_ld_steps, int(args.cpu_seconds / 3 / 0.35)))
+        per_step, sample = oracle_sample(args, data, n)
+        per_step *= max(args.members, 1)
         cpu = {"value": args.batch / (per_step * args.ld_steps), "unit": UNIT, "cores": torch.get_num_threads(),
-               "kind": "port", "us_per_eps_step": per_step * 1e6,
-               "sample": "first %d of %d Langevin steps of the same batch on the host cores (oracle port of the "
-                         "reference algorithm, dense graph build every step), extrapolated linearly" % (n, args.ld_steps)}
+               "kind": "port", "us_per_eps_step": per_step * 1e6, "sample": sample}
     ms_per_step = elapsed / args.steps * 1e3
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "strong" if ensemble_mode else "weak",
            "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "tf32", "data": "synthetic",
-           "config": dict(workload_config(args, world), l2="flushed between timed trajectories (256 MiB write)",
-                          edges_late_trajectory=mean_edges, nodes=int(data["atom_type"].numel()),
-                          edge_capacity=eng.plan.edge_capacity,
-                          network_rows_late_trajectory=eng.plan.work_count(),
-                          dedup="per-edge networks run once per unordered atom pair (both directions are "
-                                "bit-identical)" if eng.plan.upairs else "none"),
-           "us_per_eps_step": ms_per_step * 1e3 / args.ld_steps,
+           "config": workload_config(args, world), "math": args.math,
+           "run": {"l2": "flushed between timed trajectories (256 MiB write)", "edges_late_trajectory": mean_edges,
+                   "nodes": int(data["atom_type"].numel()), "edge_capacity": eng.plan.edge_capacity,
+                   "network_rows_late_trajectory": work_rows,
+                   "dedup": "per-edge networks run once per unordered atom pair (both directions are bit-identical)"
+                   if eng.plan.upairs else "none"},
+           "us_per_eps_step": ms_per_step * 1e3 / args.ld_steps / max(len(models), 1),
+           "us_per_sampler_step": ms_per_step * 1e3 / args.ld_steps,
            "gpu_launches": int(launches_per_ld_step) * args.ld_steps * args.steps,
            "launches_per_ld_step": int(launches_per_ld_step), "clocks": clock_info, "e2e": e2e,
            "roofline": tensor_roof, "roofline_message_passing": hbm_roof, "cpu_baseline": cpu,
            "published_reference_datum": "<=39.5 ms/step, ~0.51 samples/s (DDPM, unnamed GPU; BASELINE.md)"}
+    out.update(extras)
+    if ens_extra is not None:
+        out["ensemble8"] = ens_extra
     print(json.dumps(out), flush=True)
 
 

@@ -33,6 +33,17 @@
 namespace {
 using namespace tc;
 
+// -DTSD_NODE_DBG: %globaltimer stamps of cluster 0's leader (profiles/scripts/node_timeline.py); off in the product build
+#ifdef TSD_NODE_DBG
+__device__ unsigned long long g_node_dbg[64];
+#define NU_STAMP(slot)                                              \
+  do {                                                              \
+    if (blockIdx.x == 0) g_node_dbg[slot] = gtimer();               \
+  } while (0)
+#else
+#define NU_STAMP(slot) do {} while (0)
+#endif
+
 constexpr int NU_WORKERS = 16;
 constexpr int NU_THREADS = (NU_WORKERS + 2) * 32;
 constexpr int NU_MAX_SLOTS = 16;
@@ -120,31 +131,77 @@ __device__ __forceinline__ float4 nu_aggregate_item(const NodeArgs& p, const int
   return acc;
 }
 
-template <int H, int NT>
+__device__ __forceinline__ uint32_t nu_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `local` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t nu_mapa(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void nu_st_cluster4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void nu_arrive_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void nu_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+constexpr int NU_STAGE_BYTES = 16 * 1024;  // staged in-CSR ids of a CTA's atoms: 2 x 2048 entries
+
+// One cluster of C CTAs owns NT atoms.  Every CTA aggregates NT / C of them (the gathers want many SMs) and
+// stores the TF32-rounded rows straight into the LEADER's B-operand buffer through distributed shared memory;
+// then only the leader keeps its SM for the chained GEMMs (the weight stream wants few CTAs: every GEMM CTA
+// reads every W once), the other CTAs exit and free their SMs for the edge-side kernels.
+template <int H, int NT, int C>
 __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p, const __grid_constant__ NodeMaps maps,
                                                                int num_slots, int tmem_cols) {
   constexpr int MH = H / 128;                 // M = 128 halves of the output features
   constexpr int NUM_KB = H / TC_BK;           // K panels per stage
   constexpr int W_PANEL = H * TC_BK * 4;      // bytes of one W panel (H rows x 128 B)
   constexpr int X_PANEL = NT * TC_BK * 4;     // bytes of one B-operand panel (NT rows x 128 B)
-  constexpr int X_BYTES = NUM_KB * X_PANEL;   // one B operand: NT x H floats
+  constexpr int X_BYTES = NUM_KB * X_PANEL;   // the B operand: NT x H floats
   constexpr int CW = NT / 2;                  // accumulator columns per epilogue warp
+  constexpr int CWC = CW > 32 ? 32 : CW;      // ... processed in chunks of at most 32
+  constexpr int NA = NT / C;                  // atoms aggregated by one CTA
+  constexpr int NW = NU_WORKERS * 32;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t bar_full[NU_MAX_SLOTS];
   __shared__ uint64_t bar_empty[NU_MAX_SLOTS];
-  __shared__ uint64_t bar_x[2];    // B operand buffer b written (all worker threads arrive)
+  __shared__ uint64_t bar_x0;      // stage-0 B operand complete: every worker thread of every CTA of the cluster arrives
+  __shared__ uint64_t bar_xn;      // B operand of a later stage written by the leader's epilogue
   __shared__ uint64_t bar_acc[2];  // accumulator set b complete (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_ptr[NT + 1];
+  __shared__ int s_ptr[NA + 1];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int node0 = blockIdx.x * NT;
+  if (tid == 0) NU_STAMP(0);
+  const uint32_t rank = C > 1 ? nu_cluster_rank() : 0u;
+  const bool leader = rank == 0;
+  const int node0 = (blockIdx.x / C) * NT;  // first atom of the cluster's tile
   const int N = p.num_nodes;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  uint8_t* xbuf[2] = {smem_gen, smem_gen + X_BYTES};
-  uint8_t* ring = smem_gen + 2 * X_BYTES;
-  const uint32_t ring_base = smem_base + 2 * X_BYTES;
+  uint8_t* xbuf = smem_gen;                       // B operand (leader); rewritten in place by every epilogue
+  uint8_t* stage_area = smem_gen + X_BYTES;       // this CTA's staged in-CSR ids
+  uint8_t* ring = stage_area + NU_STAGE_BYTES;    // W panels (leader)
+  const uint32_t ring_base = smem_base + X_BYTES + NU_STAGE_BYTES;
   const int total_panels = p.num_stages * NUM_KB;
 
   if (tid == 0) {
@@ -152,13 +209,13 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_x[b], NU_WORKERS * 32);
-      mbar_init(&bar_acc[b], 1);
-    }
+    mbar_init(&bar_x0, C * NW);
+    mbar_init(&bar_xn, NW);
+    mbar_init(&bar_acc[0], 1);
+    mbar_init(&bar_acc[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == NU_WORKERS + 1) {
+  if (leader && warp == NU_WORKERS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"((uint32_t)tmem_cols)
                  : "memory");
@@ -167,11 +224,16 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (C > 1) {  // the leader's barriers exist before any CTA of the cluster arrives on them remotely
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   const uint32_t tmem = tmem_base_s;
+  if (tid == 0) NU_STAMP(1);
 
   if (warp == NU_WORKERS) {
-    // ------------------------------------------------------------------ TMA producer: the weights
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer: the weights (leader)
+    if (leader && lane == 0) {
       for (int s = 0; s < p.num_stages; ++s)
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[s])) : "memory");
       for (int g = 0; g < total_panels; ++g) {
@@ -182,19 +244,23 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
       }
     }
   } else if (warp == NU_WORKERS + 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader)
+    if (leader && lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(NT);
       for (int s = 0; s < p.num_stages; ++s) {
         const int b = s & 1;
-        mbar_wait(&bar_x[b], (uint32_t)((s >> 1) & 1));
+        if (s == 0) nu_wait_cluster(&bar_x0, 0);
+        else mbar_wait(&bar_xn, (uint32_t)((s - 1) & 1));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (remote) generic-proxy writes -> UMMA reads
         tc_fence_after();
+        NU_STAMP(8 + 4 * s);
         for (int kb = 0; kb < NUM_KB; ++kb) {
           const int g = s * NUM_KB + kb;
           const int slot = g % num_slots, round = g / num_slots;
           mbar_wait(&bar_full[slot], (uint32_t)(round & 1));
           tc_fence_after();
-          const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)(b * X_BYTES + kb * X_PANEL));
+          if (kb == 0) NU_STAMP(9 + 4 * s);
+          const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)(kb * X_PANEL));
 #pragma unroll
           for (int half = 0; half < MH; ++half) {
             const uint64_t adesc = umma_desc_sw128(ring_base + (uint32_t)(slot * W_PANEL + half * TC_A_PANEL_BYTES));
@@ -206,29 +272,32 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
           umma_commit(&bar_empty[slot]);
         }
         umma_commit(&bar_acc[b]);
+        NU_STAMP(10 + 4 * s);
       }
     }
   } else {
     // ------------------------------------------------------------------ workers
-    // (1) B operand of stage 0 -> xbuf[0]
+    // (1) this CTA's NA rows of the stage-0 B operand -> the leader's xbuf
     constexpr int SL = H / 128;          // 128-channel slabs per atom
-    constexpr int ITEMS = NT * SL;
+    constexpr int ITEMS = NA * SL;
+    const int my0 = (int)rank * NA;      // first row (within the tile) of this CTA
+    const uint32_t xdst = nu_mapa(smem_base, 0);  // the leader's xbuf (same offset in every CTA)
     if (p.x == nullptr) {
-      // stage the tile's in-CSR segment (contiguous: the in-CSR is sorted by target atom) in xbuf[1], which
-      // is idle until the first epilogue: the row gathers then have no dependent global index load in front
-      constexpr int CAP = X_BYTES / 8;   // entries of each of the two staged id arrays
-      int* s_eid = reinterpret_cast<int*>(xbuf[1]);
+      // stage the in-CSR segment of this CTA's atoms (contiguous: the in-CSR is sorted by target atom) in shared
+      // memory: the row gathers then have no dependent global index load in front of them
+      constexpr int CAP = NU_STAGE_BYTES / 8;
+      int* s_eid = reinterpret_cast<int*>(stage_area);
       int* s_src = s_eid + CAP;
-      for (int i = tid; i <= NT; i += NU_WORKERS * 32) s_ptr[i] = p.in_ptr[min(node0 + i, N)];
-      asm volatile("bar.sync 1, %0;" ::"r"(NU_WORKERS * 32) : "memory");
-      const int seg0 = s_ptr[0], seg_n = s_ptr[NT] - seg0;
+      for (int i = tid; i <= NA; i += NW) s_ptr[i] = p.in_ptr[min(node0 + my0 + i, N)];
+      asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
+      const int seg0 = s_ptr[0], seg_n = s_ptr[NA] - seg0;
       const bool staged = seg_n <= CAP;
       if (staged) {
-        for (int i = tid; i < seg_n; i += NU_WORKERS * 32) {
+        for (int i = tid; i < seg_n; i += NW) {
           s_eid[i] = p.in_eid[seg0 + i];
           s_src[i] = p.in_src[seg0 + i];
         }
-        asm volatile("bar.sync 1, %0;" ::"r"(NU_WORKERS * 32) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
       }
       const int* eids = staged ? s_eid - seg0 : p.in_eid;
       const int* srcs = staged ? s_src - seg0 : p.in_src;
@@ -236,90 +305,111 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
         const int n = item / SL, slab = item - n * SL;
         const int off = slab * 128 + lane * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (node0 + n < N) acc = nu_aggregate_item(p, eids, srcs, s_ptr[n], s_ptr[n + 1], off, lane);
-        *reinterpret_cast<float4*>(xbuf[0] + (size_t)(off >> 5) * X_PANEL + sw128_off(n, (off & 31) >> 2)) = tf32_rn4(acc);
+        if (node0 + my0 + n < N) acc = nu_aggregate_item(p, eids, srcs, s_ptr[n], s_ptr[n + 1], off, lane);
+        nu_st_cluster4(xdst + (uint32_t)((off >> 5) * X_PANEL) + sw128_off(my0 + n, (off & 31) >> 2), tf32_rn4(acc));
       }
-      // every worker has finished READING the staged ids before any epilogue overwrites xbuf[1]
-      asm volatile("bar.sync 1, %0;" ::"r"(NU_WORKERS * 32) : "memory");
     } else {
       for (int item = warp; item < ITEMS; item += NU_WORKERS) {
         const int n = item / SL, slab = item - n * SL;
         const int off = slab * 128 + lane * 4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)min(node0 + n, N - 1) * H + off));
-        *reinterpret_cast<float4*>(xbuf[0] + (size_t)(off >> 5) * X_PANEL + sw128_off(n, (off & 31) >> 2)) = tf32_rn4(v);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)min(node0 + my0 + n, N - 1) * H + off));
+        nu_st_cluster4(xdst + (uint32_t)((off >> 5) * X_PANEL) + sw128_off(my0 + n, (off & 31) >> 2), tf32_rn4(v));
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
-    mbar_arrive(&bar_x[0]);
+    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async proxy (the leader's UMMA)
+    nu_arrive_cluster(nu_mapa(smem_u32(&bar_x0), 0));
+    if (tid == 0) NU_STAMP(2);
 
-    // (2) epilogues.  warp -> TMEM lane quarter q (hardware: warp_id % 4), output-feature half, column half
-    const int q = warp & 3, half = (warp >> 2) & 1, cs = warp >> 3;
-    const bool epi_warp = half < MH;  // H = 128: one M half, warps with half == 1 only take part in the barriers
-    const int f = half * 128 + q * 32 + lane;
-    const int n0 = cs * CW;
-    for (int s = 0; s < p.num_stages; ++s) {
-      const int b = s & 1;
-      const NodeStage& st = p.st[s];
-      const bool feeds = s + 1 < p.num_stages;
-      float res[CW];
-      float bias = 0.f;
-      if (epi_warp) {
-        // operands of the epilogue that do not depend on the accumulator: in flight behind the MMA
-        if (st.bias) bias = __ldg(st.bias + f);
-        if (st.residual) {
+    if (leader) {
+      // (2) epilogues.  warp -> TMEM lane quarter q (hardware: warp_id % 4), output-feature half, column half
+      const int q = warp & 3, half = (warp >> 2) & 1, cs = warp >> 3;
+      const bool epi_warp = half < MH;  // H = 128: one M half, warps with half == 1 only take part in the barriers
+      const int f = half * 128 + q * 32 + lane;
+      for (int s = 0; s < p.num_stages; ++s) {
+        const int b = s & 1;
+        const NodeStage& st = p.st[s];
+        const bool feeds = s + 1 < p.num_stages;
+        float bias = 0.f;
+        if (epi_warp && st.bias) bias = __ldg(st.bias + f);
+        bool waited = false;
+#pragma unroll 1
+        for (int cc = 0; cc < CW; cc += CWC) {
+          const int n0 = cs * CW + cc;
+          float res[CWC];
+          if (epi_warp && st.residual) {  // independent of the accumulator: in flight behind the MMA
 #pragma unroll
-          for (int j = 0; j < CW; ++j) res[j] = st.residual[(size_t)min(node0 + n0 + j, N - 1) * H + f];
-        }
-      }
-      mbar_wait(&bar_acc[b], (uint32_t)((s >> 1) & 1));
-      tc_fence_after();
-      if (epi_warp) {
-        uint32_t v[CW];
-        tmem_ld_cols<CW>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * MH + half) * NT + n0), v);
-        uint8_t* xn = xbuf[b ^ 1] + (size_t)(f >> 5) * X_PANEL + (size_t)((f & 3) << 2);
-        const int chunk = (f & 31) >> 2;
+            for (int j = 0; j < CWC; ++j) res[j] = st.residual[(size_t)min(node0 + n0 + j, N - 1) * H + f];
+          }
+          if (!waited) {
+            mbar_wait(&bar_acc[b], (uint32_t)((s >> 1) & 1));
+            tc_fence_after();
+            waited = true;
+            if (tid == 0) NU_STAMP(11 + 4 * s);
+          }
+          if (epi_warp) {
+            uint32_t v[CWC];
+            tmem_ld_cols<CWC>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * MH + half) * NT + n0), v);
+            uint8_t* xn = xbuf + (size_t)(f >> 5) * X_PANEL + (size_t)((f & 3) << 2);
+            const int chunk = (f & 31) >> 2;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          float r = __uint_as_float(v[j]) + bias;
-          if (st.act == TSD_ACT_SSP) r = tc_act<TSD_ACT_SSP>(r);
-          if (st.residual) r += res[j];
-          const int n = n0 + j;
-          if (st.store && node0 + n < N) st.store[(size_t)(node0 + n) * H + f] = r;
-          if (feeds) *reinterpret_cast<float*>(xn + n * 128 + ((chunk ^ (n & 7)) << 4)) = tf32_rn(r);
+            for (int j = 0; j < CWC; ++j) {
+              float r = __uint_as_float(v[j]) + bias;
+              if (st.act == TSD_ACT_SSP) r = tc_act<TSD_ACT_SSP>(r);
+              if (st.residual) r += res[j];
+              const int n = n0 + j;
+              if (st.store && node0 + n < N) st.store[(size_t)(node0 + n) * H + f] = r;
+              if (feeds) *reinterpret_cast<float*>(xn + n * 128 + ((chunk ^ (n & 7)) << 4)) = tf32_rn(r);
+            }
+          }
         }
-      }
-      if (feeds) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(&bar_x[b ^ 1]);
+        if (feeds) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(&bar_xn);
+        }
+        if (tid == 0) NU_STAMP(3 + s);
       }
     }
   }
+  if (!leader) return;  // the other CTAs of the cluster only aggregate
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) NU_STAMP(6);
   if (warp == NU_WORKERS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols)
                  : "memory");
   }
 }
 
-template <int H, int NT>
+template <int H, int NT, int C>
 int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
   constexpr int W_PANEL = H * TC_BK * 4, X_BYTES = NT * H * 4, NUM_KB = H / TC_BK;
-  const int budget = 227 * 1024 - 2 * X_BYTES - 1024 - 2048;  // alignment slack + static shared memory
+  const int budget = 227 * 1024 - X_BYTES - NU_STAGE_BYTES - 1024 - 2048;  // alignment slack + static shared memory
   int slots = budget / W_PANEL;
   if (slots > a.num_stages * NUM_KB) slots = a.num_stages * NUM_KB;
   if (slots > NU_MAX_SLOTS) slots = NU_MAX_SLOTS;
   if (slots < 2) return TSD_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)2 * X_BYTES + (size_t)slots * W_PANEL + 1024;
+  const size_t smem = (size_t)X_BYTES + NU_STAGE_BYTES + (size_t)slots * W_PANEL + 1024;
   static size_t attr_smem = 0;  // per instantiation
   if (smem > attr_smem) {
-    TSD_CUDA(cudaFuncSetAttribute(k_node_update<H, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSD_CUDA(cudaFuncSetAttribute(k_node_update<H, NT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   int tmem_cols = 2 * (H / 128) * NT;
   if (tmem_cols < 32) tmem_cols = 32;
-  k_node_update<H, NT><<<tsd_ceil_div(a.num_nodes, NT), NU_THREADS, smem, stream>>>(a, maps, slots, tmem_cols);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tsd_ceil_div(a.num_nodes, NT) * C);
+  cfg.blockDim = dim3(NU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TSD_CUDA(cudaLaunchKernelEx(&cfg, k_node_update<H, NT, C>, a, maps, slots, tmem_cols));
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }
@@ -328,14 +418,17 @@ int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
 
 // Rows per CTA: enough CTAs to spread the aggregation's gathers over the GPU, few enough that the weight
 // stream (every CTA reads every W once) stays small against them.
+#ifdef TSD_NODE_DBG
+extern "C" void tsd_node_dbg_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_node_dbg, sizeof(g_node_dbg)); }
+#endif
 static int g_node_tile_override = 0;
 // tuning hook of profiles/scripts (not part of the C-ABI header): 0 restores the built-in choice
 extern "C" void tsd_tune_node_tile(int tile) { g_node_tile_override = tile; }
 
+// Atoms per cluster (16 per CTA): clusters of 4 give 28 GEMM CTAs at batch 100 (~1750 atoms)
 int tsd_node_tile(int num_nodes) {
   if (g_node_tile_override == 16 || g_node_tile_override == 32 || g_node_tile_override == 64) return g_node_tile_override;
-  if (num_nodes <= 16 * 148) return 16;
-  if (num_nodes <= 32 * 148) return 32;
+  (void)num_nodes;
   return 64;
 }
 
@@ -352,11 +445,11 @@ int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
     if (!make_tensor_map(&maps.w[s], w, (uint64_t)a.H, (uint64_t)a.H, (uint32_t)a.H)) return TSD_ERR_UNSUPPORTED;
   }
   if (a.H == 256) {
-    if (tile == 16) return node_launch<256, 16>(a, maps, stream);
-    if (tile == 32) return node_launch<256, 32>(a, maps, stream);
-    return node_launch<256, 64>(a, maps, stream);
+    if (tile == 16) return node_launch<256, 16, 1>(a, maps, stream);
+    if (tile == 32) return node_launch<256, 32, 2>(a, maps, stream);
+    return node_launch<256, 64, 4>(a, maps, stream);
   }
-  if (tile == 16) return node_launch<128, 16>(a, maps, stream);
-  if (tile == 32) return node_launch<128, 32>(a, maps, stream);
-  return node_launch<128, 64>(a, maps, stream);
+  if (tile == 16) return node_launch<128, 16, 1>(a, maps, stream);
+  if (tile == 32) return node_launch<128, 32, 2>(a, maps, stream);
+  return node_launch<128, 64, 4>(a, maps, stream);
 }
