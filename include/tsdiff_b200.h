@@ -212,11 +212,15 @@ int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* edges, const
  * fused_w / fused_b set on every block but the last, the node update is split: the critical
  * kernel of a block computes only x1_next = lin1_next(h) + fused_w ssp(lin2(agg)) + fused_b (two
  * chained GEMMs), while h' = h + lin(ssp(lin2(agg))) and lin1 of the block after next run beside
- * the next aggregation.  h_in is not modified; h_out may not alias h_in. */
+ * the next aggregation.  h_in is not modified; h_out may not alias h_in.
+ * ef_pool (optional): ef_pool_count x (E_cap, H) extra filter buffers.  The filter network of a block only depends
+ * on edge_attr, so with one buffer per block (2 + ef_pool_count >= num_blocks) the edge-side kernels of ALL blocks
+ * run ahead of the serial node-side chain instead of waiting for the block that last used their buffer. */
 int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                        const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
                        float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* nf_pool,
-                       int32_t nf_pool_count, int32_t math, tsd_stream_t stream);
+                       int32_t nf_pool_count, float* ef_pool, int32_t ef_pool_count, int32_t math,
+                       tsd_stream_t stream);
 
 /* The two building blocks of K4, exposed on their own for unit tests and for the per-kernel
  * roofline timing in bench.py:
@@ -326,6 +330,23 @@ int tsd_eq_transform(const tsd_batch_t* batch, const tsd_edges_t* edges, const f
 /* Philox4x32-10 + Box-Muller normals exactly as tsd_ld_step draws them: out (N,3). */
 int tsd_philox_normal(int32_t num_nodes, uint64_t seed, int32_t step, int64_t atom_offset,
                       float* out, tsd_stream_t stream);
+
+/* ---- post-sampling geometry metrics, fp64 like the reference's numpy / scipy code.
+ * tsd_dmae (clustering.py:98-105 `calc_DMAE`): out[b] = sum over i < j of |dm_ref - dm_guess[b]| (mape: / dm_ref),
+ *   divided by n (n - 1) / 2; dm_ref (n, n), dm_guess (batch, n, n).  tsd_dmae_pos: the same from positions
+ *   pos_ref (n, 3), pos_guess (batch, n, 3).
+ * tsd_min_match (clustering.py:123-135 `get_minimum_matches` with its default metric): for every probe geometry b
+ *   out_val[b] = min over the permutations m of sum_{i<j} (|ref_i - ref_j| - |prb[b][match[m][i]] - prb[b][match[m][j]]|)^2,
+ *   out_idx[b] = the first arg-min (list.index(min(...))).  matches (num_matches, n) int32.  Scratch sizes come
+ *   from tsd_min_match_scratch (elements, not bytes). */
+int tsd_dmae(int32_t num_atoms, int32_t batch, const double* dm_ref, const double* dm_guess, int32_t mape, double* out,
+             tsd_stream_t stream);
+int tsd_dmae_pos(int32_t num_atoms, int32_t batch, const double* pos_ref, const double* pos_guess, int32_t mape,
+                 double* out, tsd_stream_t stream);
+int tsd_min_match_scratch(int32_t batch, int32_t num_matches, int64_t* doubles, int64_t* ints);
+int tsd_min_match(int32_t num_atoms, int32_t batch, int32_t num_matches, const double* pos_ref, const double* pos_prb,
+                  const int32_t* matches, double* scratch_val, int32_t* scratch_idx, double* out_val, int32_t* out_idx,
+                  tsd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -91,7 +91,7 @@ _SIGNATURES = {
                          C.c_int32, _P],
     "tsd_filter_network": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Interaction), _P, _P, C.c_int32, _P],
     "tsd_schnet_encoder": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Interaction), C.c_int32, _P, _P, _P, _P,
-                           _P, _P, _P, _P, C.c_int32, C.c_int32, _P],
+                           _P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P],
     "tsd_gine_layer": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Gine), _P, _P, _P, _P, C.c_int32, _P],
     "tsd_pair_mlp": [C.POINTER(Batch), C.POINTER(Edges), _P, _P, C.POINTER(PairMlp), C.c_int32, _P, _P, C.c_int32,
                      _P],
@@ -99,6 +99,10 @@ _SIGNATURES = {
                     C.POINTER(LdParams), _P],
     "tsd_eq_transform": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.c_float, _P, _P],
     "tsd_philox_normal": [C.c_int32, C.c_uint64, C.c_int32, C.c_int64, _P, _P],
+    "tsd_dmae": [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P],
+    "tsd_dmae_pos": [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P],
+    "tsd_min_match_scratch": [C.c_int32, C.c_int32, _P, _P],
+    "tsd_min_match": [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 _RESTYPES = {"tsd_error_string": C.c_char_p, "tsd_launch_count": C.c_int64}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -371,7 +371,8 @@ extern "C" int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* e
 extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                                   const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
                                   float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* nf_pool,
-                                  int32_t nf_pool_count, int32_t math, tsd_stream_t stream) {
+                                  int32_t nf_pool_count, float* ef_pool, int32_t ef_pool_count, int32_t math,
+                                  tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && edge_attr && blocks && num_blocks >= 1 && h_in && h_out && ef0 && ef1 && nf0 && nf1 && nf2);
   cudaStream_t s = tsd_cu(stream);
   const int H = blocks[0].lin.out_features;
@@ -413,13 +414,21 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
   std::lock_guard<std::mutex> fk_lock(fk_mutex);
   TSD_TRY(fk.init(num_blocks));
   cudaStream_t side = fk.side, side2 = fk.side2;
-  if (tsd_ceil_div(batch->num_nodes, 64) <= 148) {
+  if (!TSD_EXP_OLD_NODE && tsd_ceil_div(batch->num_nodes, 16) <= 4 * 148) {
     // Few atoms (batch 100: ~1750): the node side of every block is ONE kernel of N/NT small CTAs -- the
     // aggregation fused in front of the three linears as transposed (swap-AB) tensor-core GEMMs
     // (node_update.cu).  x1 ping-pongs between nf0 and nf1: a CTA's aggregation gathers x1 rows of atoms
     // that other CTAs own, so the next block's x1 must not overwrite them.
     const int tile = tsd_node_tile(batch->num_nodes);
     float* x1buf[2] = {nf0, nf1};
+    // filter buffers: ef1, ef0, then the optional pool (one per block lets every filter kernel run ahead)
+    float* fbuf[EncoderFork::MAX_BLOCKS];
+    int nbuf = 0;
+    fbuf[nbuf++] = ef1;
+    fbuf[nbuf++] = ef0;
+    const size_t edge_elems = (size_t)(batch->edge_capacity > 0 ? batch->edge_capacity : 1) * H;
+    for (int i = 0; TSD_EXP_FILTER_POOL && ef_pool && i < ef_pool_count && nbuf < num_blocks; ++i)
+      fbuf[nbuf++] = ef_pool + (size_t)i * edge_elems;
     TSD_CUDA(cudaEventRecord(fk.fork, s));
     TSD_CUDA(cudaStreamWaitEvent(side, fk.fork, 0));
     NodeArgs na;
@@ -433,8 +442,8 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     TSD_TRY(tsd_node_update_tf32(na, tile, side));
     for (int l = 0; l < num_blocks; ++l) {
       const tsd_interaction_t& b = blocks[l];
-      float* filt = (l & 1) ? ef0 : ef1;
-      if (l >= 2) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - 2], 0));  // buffer reuse: block l-2 has read it
+      float* filt = fbuf[l % nbuf];
+      if (l >= nbuf) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - nbuf], 0));  // buffer reuse: that block has read it
       ChainArgs c;
       memset(&c, 0, sizeof(c));
       c.M_cap = batch->edge_capacity;

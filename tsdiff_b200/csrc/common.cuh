@@ -5,6 +5,13 @@
 
 #include "../../include/tsdiff_b200.h"
 
+// compile-time switches of profiles/scripts/variants.py (A/B measurements behind DESIGN.md section 8)
+#ifndef TSD_EXP_OLD_NODE
+#define TSD_EXP_OLD_NODE 0     // 1: node side of the encoder as in round 1 (aggregation kernel + 128-row chained kernels)
+#endif
+#ifndef TSD_EXP_FILTER_POOL
+#define TSD_EXP_FILTER_POOL 1  // one filter buffer per block: the filter kernels run ahead of the node-side chain
+#endif
 #define TSD_WARP 32
 #define TSD_FULL_MASK 0xffffffffu
 

@@ -177,6 +177,8 @@ __device__ __forceinline__ void chain_stage_run(const ChainArgs& p, const ChainM
       const uint32_t slot = c.ring_base + (uint32_t)s * c.w_panel_bytes;
       const uint64_t adesc = umma_desc_sw128(c.smem_base + (uint32_t)kb * TC_A_PANEL_BYTES);
       const uint64_t bdesc = umma_desc_sw128(slot);
+      // (two N = H/2 MMAs per K step on disjoint accumulator columns issue faster in isolation -- 128 instead of
+      // 171 clk per K step, profiles/r2_umma_small_n.txt -- but read the A panel twice: 10 us slower per Langevin step)
 #pragma unroll
       for (int kk = 0; kk < TC_BK / 8; ++kk)
         umma_tf32(acc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), c.idesc, (kb | kk) != 0 ? 1u : 0u);

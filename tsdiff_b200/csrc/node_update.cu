@@ -47,6 +47,7 @@ __device__ unsigned long long g_node_dbg[64];
 constexpr int NU_WORKERS = 16;
 constexpr int NU_THREADS = (NU_WORKERS + 2) * 32;
 constexpr int NU_MAX_SLOTS = 16;
+constexpr int NU_SLOT_PANELS = 2;
 
 struct NodeMaps {
   CUtensorMap w[3];
@@ -175,10 +176,13 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
   constexpr int MH = H / 128;                 // M = 128 halves of the output features
   constexpr int NUM_KB = H / TC_BK;           // K panels per stage
   constexpr int W_PANEL = H * TC_BK * 4;      // bytes of one W panel (H rows x 128 B)
+  constexpr int KP = NU_SLOT_PANELS;          // K panels per ring slot: one tcgen05.commit (~250 clk of tensor-pipe
+  constexpr int W_SLOT = KP * W_PANEL;        // time when the MMAs are short) releases KP panels
+  constexpr int NUM_KS = NUM_KB / KP;         // slots per stage
   constexpr int X_PANEL = NT * TC_BK * 4;     // bytes of one B-operand panel (NT rows x 128 B)
   constexpr int X_BYTES = NUM_KB * X_PANEL;   // the B operand: NT x H floats
   constexpr int CW = NT / 2;                  // accumulator columns per epilogue warp
-  constexpr int CWC = CW > 32 ? 32 : CW;      // ... processed in chunks of at most 32
+  constexpr int CWC = CW % 32 == 0 ? 32 : (CW % 16 == 0 ? 16 : 8);  // ... processed in chunks of 32 / 16 / 8
   constexpr int NA = NT / C;                  // atoms aggregated by one CTA
   constexpr int NW = NU_WORKERS * 32;
   extern __shared__ uint8_t smem_dyn[];
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
   uint8_t* stage_area = smem_gen + X_BYTES;       // this CTA's staged in-CSR ids
   uint8_t* ring = stage_area + NU_STAGE_BYTES;    // W panels (leader)
   const uint32_t ring_base = smem_base + X_BYTES + NU_STAGE_BYTES;
-  const int total_panels = p.num_stages * NUM_KB;
+  const int total_slots = p.num_stages * NUM_KS;
 
   if (tid == 0) {
     for (int s = 0; s < num_slots; ++s) {
@@ -236,11 +240,14 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
     if (leader && lane == 0) {
       for (int s = 0; s < p.num_stages; ++s)
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[s])) : "memory");
-      for (int g = 0; g < total_panels; ++g) {
+      for (int g = 0; g < total_slots; ++g) {
         const int slot = g % num_slots, round = g / num_slots;
         if (round > 0) mbar_wait(&bar_empty[slot], (uint32_t)((round - 1) & 1));
-        mbar_arrive_expect_tx(&bar_full[slot], (uint32_t)W_PANEL);
-        tma_load_2d(ring + (size_t)slot * W_PANEL, &maps.w[g / NUM_KB], &bar_full[slot], (g % NUM_KB) * TC_BK, 0);
+        mbar_arrive_expect_tx(&bar_full[slot], (uint32_t)W_SLOT);
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          tma_load_2d(ring + (size_t)slot * W_SLOT + (size_t)k * W_PANEL, &maps.w[g / NUM_KS], &bar_full[slot],
+                      ((g % NUM_KS) * KP + k) * TC_BK, 0);
       }
     }
   } else if (warp == NU_WORKERS + 1) {
@@ -254,20 +261,28 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (remote) generic-proxy writes -> UMMA reads
         tc_fence_after();
         NU_STAMP(8 + 4 * s);
-        for (int kb = 0; kb < NUM_KB; ++kb) {
-          const int g = s * NUM_KB + kb;
+        for (int ks = 0; ks < NUM_KS; ++ks) {
+          const int g = s * NUM_KS + ks;
           const int slot = g % num_slots, round = g / num_slots;
           mbar_wait(&bar_full[slot], (uint32_t)(round & 1));
           tc_fence_after();
-          if (kb == 0) NU_STAMP(9 + 4 * s);
-          const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)(kb * X_PANEL));
+          if (ks == 0) NU_STAMP(9 + 4 * s);
 #pragma unroll
-          for (int half = 0; half < MH; ++half) {
-            const uint64_t adesc = umma_desc_sw128(ring_base + (uint32_t)(slot * W_PANEL + half * TC_A_PANEL_BYTES));
-            const uint32_t acc = tmem + (uint32_t)((b * MH + half) * NT);
+          for (int k = 0; k < KP; ++k) {
+            const int kb = ks * KP + k;
+            const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)(kb * X_PANEL));
+            // consecutive MMAs alternate between the accumulators of the two M halves (MMAs into the same
+            // accumulator serialise: 94 clk each instead of 47 at small N; profiles/r2_umma_small_n.txt)
 #pragma unroll
-            for (int kk = 0; kk < TC_BK / 8; ++kk)
-              umma_tf32(acc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < TC_BK / 8; ++kk) {
+#pragma unroll
+              for (int half = 0; half < MH; ++half) {
+                const uint64_t adesc =
+                    umma_desc_sw128(ring_base + (uint32_t)(slot * W_SLOT + k * W_PANEL + half * TC_A_PANEL_BYTES));
+                umma_tf32(tmem + (uint32_t)((b * MH + half) * NT), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk),
+                          idesc, (kb | kk) != 0 ? 1u : 0u);
+              }
+            }
           }
           umma_commit(&bar_empty[slot]);
         }
@@ -327,18 +342,23 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
       const int f = half * 128 + q * 32 + lane;
       for (int s = 0; s < p.num_stages; ++s) {
         const int b = s & 1;
-        const NodeStage& st = p.st[s];
+        // the stage description in REGISTERS: indexing p.st[] at run time puts it in local memory, and every
+        // generic-address store below would force a reload of each field (measured: ~200 clk per element)
+        const float* const st_bias = p.st[s].bias;
+        const float* const st_res = p.st[s].residual;
+        float* const st_store = p.st[s].store;
+        const bool st_ssp = p.st[s].act == TSD_ACT_SSP;
         const bool feeds = s + 1 < p.num_stages;
         float bias = 0.f;
-        if (epi_warp && st.bias) bias = __ldg(st.bias + f);
+        if (epi_warp && st_bias) bias = __ldg(st_bias + f);
         bool waited = false;
 #pragma unroll 1
         for (int cc = 0; cc < CW; cc += CWC) {
           const int n0 = cs * CW + cc;
           float res[CWC];
-          if (epi_warp && st.residual) {  // independent of the accumulator: in flight behind the MMA
+          if (epi_warp && st_res) {  // independent of the accumulator: in flight behind the MMA
 #pragma unroll
-            for (int j = 0; j < CWC; ++j) res[j] = st.residual[(size_t)min(node0 + n0 + j, N - 1) * H + f];
+            for (int j = 0; j < CWC; ++j) res[j] = st_res[(size_t)min(node0 + n0 + j, N - 1) * H + f];
           }
           if (!waited) {
             mbar_wait(&bar_acc[b], (uint32_t)((s >> 1) & 1));
@@ -354,10 +374,10 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
 #pragma unroll
             for (int j = 0; j < CWC; ++j) {
               float r = __uint_as_float(v[j]) + bias;
-              if (st.act == TSD_ACT_SSP) r = tc_act<TSD_ACT_SSP>(r);
-              if (st.residual) r += res[j];
+              if (st_ssp) r = tc_act<TSD_ACT_SSP>(r);
+              if (st_res) r += res[j];
               const int n = n0 + j;
-              if (st.store && node0 + n < N) st.store[(size_t)(node0 + n) * H + f] = r;
+              if (st_store && node0 + n < N) st_store[(size_t)(node0 + n) * H + f] = r;
               if (feeds) *reinterpret_cast<float*>(xn + n * 128 + ((chunk ^ (n & 7)) << 4)) = tf32_rn(r);
             }
           }
@@ -383,13 +403,13 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
 
 template <int H, int NT, int C>
 int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
-  constexpr int W_PANEL = H * TC_BK * 4, X_BYTES = NT * H * 4, NUM_KB = H / TC_BK;
+  constexpr int W_SLOT = NU_SLOT_PANELS * H * TC_BK * 4, X_BYTES = NT * H * 4, NUM_KS = H / TC_BK / NU_SLOT_PANELS;
   const int budget = 227 * 1024 - X_BYTES - NU_STAGE_BYTES - 1024 - 2048;  // alignment slack + static shared memory
-  int slots = budget / W_PANEL;
-  if (slots > a.num_stages * NUM_KB) slots = a.num_stages * NUM_KB;
+  int slots = budget / W_SLOT;
+  if (slots > a.num_stages * NUM_KS) slots = a.num_stages * NUM_KS;
   if (slots > NU_MAX_SLOTS) slots = NU_MAX_SLOTS;
   if (slots < 2) return TSD_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)X_BYTES + NU_STAGE_BYTES + (size_t)slots * W_PANEL + 1024;
+  const size_t smem = (size_t)X_BYTES + NU_STAGE_BYTES + (size_t)slots * W_SLOT + 1024;
   static size_t attr_smem = 0;  // per instantiation
   if (smem > attr_smem) {
     TSD_CUDA(cudaFuncSetAttribute(k_node_update<H, NT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -422,14 +442,15 @@ int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
 extern "C" void tsd_node_dbg_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_node_dbg, sizeof(g_node_dbg)); }
 #endif
 static int g_node_tile_override = 0;
-// tuning hook of profiles/scripts (not part of the C-ABI header): 0 restores the built-in choice
-extern "C" void tsd_tune_node_tile(int tile) { g_node_tile_override = tile; }
+// tuning hook of profiles/scripts (not part of the C-ABI header): code = atoms per cluster * 10 + CTAs per cluster,
+// 0 restores the built-in choice
+extern "C" void tsd_tune_node_tile(int code) { g_node_tile_override = code; }
 
-// Atoms per cluster (16 per CTA): clusters of 4 give 28 GEMM CTAs at batch 100 (~1750 atoms)
+// atoms per cluster * 10 + CTAs per cluster
 int tsd_node_tile(int num_nodes) {
-  if (g_node_tile_override == 16 || g_node_tile_override == 32 || g_node_tile_override == 64) return g_node_tile_override;
+  if (g_node_tile_override > 0) return g_node_tile_override;
   (void)num_nodes;
-  return 64;
+  return 321;  // 32 atoms per CTA: at batch 100 the 55 node CTAs fit beside the 94 filter tiles (profiles/r2_variants.txt)
 }
 
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
@@ -444,12 +465,14 @@ int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
     if (reinterpret_cast<uintptr_t>(w) & 15) return TSD_ERR_UNSUPPORTED;
     if (!make_tensor_map(&maps.w[s], w, (uint64_t)a.H, (uint64_t)a.H, (uint32_t)a.H)) return TSD_ERR_UNSUPPORTED;
   }
-  if (a.H == 256) {
-    if (tile == 16) return node_launch<256, 16, 1>(a, maps, stream);
-    if (tile == 32) return node_launch<256, 32, 2>(a, maps, stream);
-    return node_launch<256, 64, 4>(a, maps, stream);
-  }
-  if (tile == 16) return node_launch<128, 16, 1>(a, maps, stream);
-  if (tile == 32) return node_launch<128, 32, 2>(a, maps, stream);
-  return node_launch<128, 64, 4>(a, maps, stream);
+#define NU_GO(NT, C)                                                  \
+  if (tile == NT * 10 + C)                                            \
+    return a.H == 256 ? node_launch<256, NT, C>(a, maps, stream) : node_launch<128, NT, C>(a, maps, stream)
+  NU_GO(16, 1);
+  NU_GO(32, 1);
+  NU_GO(64, 1);
+  NU_GO(32, 2);
+  NU_GO(64, 4);
+#undef NU_GO
+  return TSD_ERR_UNSUPPORTED;
 }

@@ -123,7 +123,10 @@ template <int ACT>
 __device__ __forceinline__ float tc_act(float x) {
   if (ACT == TSD_ACT_RELU) return fmaxf(x, 0.f);
   if (ACT == TSD_ACT_SWISH) return __fdividef(x, 1.f + __expf(-x));
-  // branch-free softplus: max(x,0) + log(1 + exp(-|x|))
+  // branch-free shifted softplus: max(x,0) + log1p(exp(-|x|)) - ln 2
+  // branch-free softplus: max(x,0) + log(1 + exp(-|x|)).  (Measured, profiles/r2_variants.txt: replacing the lg2 by an
+  // FMA-pipe polynomial and the cvt.rna.tf32 by two ALU operations changed nothing -- the epilogues are bound by
+  // instruction issue, not by the XU pipe.)
   if (ACT == TSD_ACT_SSP) return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))) - TSD_SSP_SHIFT;
   if (ACT == TSD_ACT_SOFTPLUS) return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
   return x;

@@ -233,6 +233,15 @@ def _node_pool(plan, hidden, math):
     return torch.empty(2 * max(plan.num_nodes, 1) * hidden, dtype=torch.float32, device=plan.device), 2
 
 
+def _filter_pool(plan, hidden, num_blocks, math):
+    """tf32 mode: one filter buffer per interaction block beyond the two of the workspace, so the filter networks of
+    all blocks (they only depend on edge_attr) run ahead of the serial node-side chain (tsd_schnet_encoder)."""
+    extra = max(num_blocks - 2, 0)
+    if math != "tf32" or extra == 0:
+        return None, 0
+    return torch.empty(extra * max(plan.work_capacity, 1) * hidden, dtype=torch.float32, device=plan.device), extra
+
+
 def _edge_encoder_struct(enc, act, cat=None, cat_act="none", wv=lambda w: w):
     """enc: layers.MLPEdgeEncoder; cat: nn.Sequential(Linear, act, Linear) or None."""
     keep = []
@@ -332,6 +341,7 @@ class CondensedScoreEngine:
         self.ws = _Scratch(plan, h, 7, 4, 0, math)
         self.side = torch.cuda.Stream(device=plan.device)  # second-graph edge embedding runs beside the encoder
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
+        self.ef_pool, self.ef_pool_count = _filter_pool(plan, h, len(models[0].encoder.interactions), math)
         self.edge_inv = torch.zeros(max(plan.work_capacity, 1), dtype=torch.float32, device=plan.device)
         atom_type = atom_type.to(torch.long).contiguous()
         r_feat = _integer_features(r_feat, "r_feat")
@@ -370,7 +380,8 @@ class CondensedScoreEngine:
                 fork.record(main)
             L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
                                            L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                           L.ptr(self.nf_pool), self.nf_pool_count, self.math, s),
+                                           L.ptr(self.nf_pool), self.nf_pool_count, L.ptr(self.ef_pool),
+                                           self.ef_pool_count, self.math, s),
                     "tsd_schnet_encoder")
             if self.two_graphs:
                 # the pred_edge_order graph's edge embedding only needs d_emb and is only read by the pair
@@ -452,6 +463,7 @@ class DualScoreEngine:
         self.ws = _Scratch(plan, h, 7, 7, 1, math)
         self.side = torch.cuda.Stream(device=plan.device)  # the local (GIN) branch runs beside the global one
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
+        self.ef_pool, self.ef_pool_count = _filter_pool(plan, h, len(model.encoder_global.interactions), math)
         cap = max(plan.work_capacity, 1)  # rows of the per-edge networks: unordered pairs when plan.upairs
         # TS variant (edge_cat): the local edge encoder needs its own d_emb / tmp scratch
         self.local_scratch = ([torch.empty(cap, h, dtype=torch.float32, device=plan.device) for _ in range(2)]
@@ -518,7 +530,8 @@ class DualScoreEngine:
                                    self.math, s), "tsd_edge_embed")
         L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea_g), self.blocks, len(self.blocks), L.ptr(self.h0_global),
                                        L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
-                                       L.ptr(self.nf_pool), self.nf_pool_count, self.math, s), "tsd_schnet_encoder")
+                                       L.ptr(self.nf_pool), self.nf_pool_count, L.ptr(self.ef_pool), self.ef_pool_count,
+                                       self.math, s), "tsd_schnet_encoder")
         L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
                                  L.ptr(self.edge_inv_global), self.math, s), "tsd_pair_mlp")
         main.wait_stream(self.side)
