@@ -187,7 +187,7 @@ def oracle_sample(args, data, n_per_window):
 
 def workload_config(args, world):
     if args.mode == "ensemble":
-        sharding = "%d ensemble members over %d GPU(s), same batch on every rank, per-step score exchange" % (
+        sharding = "%d ensemble members over %d GPU(s), same batch on every rank, per-step score exchange fused into K7" % (
             args.members, world)
     else:
         sharding = "reactions x%d, no collective" % world
@@ -234,7 +234,7 @@ def flush_l2(buf):
     buf.zero_()
 
 
-def build_runner(args, models, data_dev, keep_traj=True, math=None, reduce=None, ensemble_size=None):
+def build_runner(args, models, data_dev, keep_traj=True, math=None, reduce=None, ensemble_size=None, exchange_group=None):
     """Device-resident sampler state: engine + CUDA-graph runner, inputs already in HBM."""
     from tsdiff_b200 import engine as E
     d = data_dev
@@ -251,8 +251,9 @@ def build_runner(args, models, data_dev, keep_traj=True, math=None, reduce=None,
         sched, sigmas = E.ld_schedule(model.alphas, args.ld_steps, 1e-7)
         ch0, ch1 = eng.score_channels(10.0, 10.0, 0.2)
     pos = (d["pos_init"] * sigmas[-1].to(d["pos_init"].device)).contiguous()
+    exchange = E.PeerExchange(eng.plan, exchange_group) if exchange_group is not None else None
     runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, seed=2022, keep_traj=keep_traj, reduce=reduce,
-                              ensemble_size=ensemble_size)
+                              ensemble_size=ensemble_size, exchange=exchange)
     return eng, runner
 
 
@@ -440,24 +441,35 @@ def measure_ensemble(args, rank, world, device, group, flush_buf, members=8):
     data_dev = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
     seeds = [m for m in range(members) if m % world == rank]
     models = [make_models(args, device, seed=sd)[0] for sd in seeds]
-    reduce = (lambda t: dist.all_reduce(t, group=group)) if world > 1 else None  # noqa: E731
-    eng, runner = build_runner(args, models, data_dev, keep_traj=False, reduce=reduce,
-                               ensemble_size=members if world > 1 else None)
-    runner.prepare()
-    runner.run(n_steps=20)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t = torch.tensor([full_trajectory(runner, flush_buf)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t = float(t.item())
-    checksum = float(runner.pos.double().abs().sum())
-    del runner, eng  # a captured graph with NCCL nodes must be released before the process group goes away
-    return {"value": args.batch / t, "unit": UNIT, "members": members, "members_per_gpu": len(seeds), "n_gpus": world,
-            "us_per_sampler_step": t * 1e6 / args.ld_steps, "trajectories": 1, "ld_steps": args.ld_steps,
-            "exchange": "none (one GPU)" if world == 1 else "NCCL all-reduce of the (N,3) partial scores, captured in the step graph",
-            "final_pos_abs_sum": checksum}
+    out = {"unit": UNIT, "members": members, "members_per_gpu": len(seeds), "n_gpus": world, "trajectories": 1,
+           "ld_steps": args.ld_steps}
+    kinds = ["none"] if world == 1 else ["fused", "nccl"]
+    for kind in kinds:
+        reduce = (lambda t: dist.all_reduce(t, group=group)) if kind == "nccl" else None  # noqa: E731
+        eng, runner = build_runner(args, models, data_dev, keep_traj=False, reduce=reduce,
+                                   ensemble_size=members if world > 1 else None, exchange_group=group if kind == "fused" else None)
+        runner.prepare()
+        runner.run(n_steps=20)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([full_trajectory(runner, flush_buf)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = float(t.item())
+        checksum = float(runner.pos.double().abs().sum())
+        ex = runner.exchange
+        del runner, eng  # a captured graph with NCCL nodes must be released before the process group goes away
+        if ex is not None:
+            ex.close()
+        res = {"value": args.batch / t, "us_per_sampler_step": t * 1e6 / args.ld_steps, "final_pos_abs_sum": checksum}
+        if kind == "nccl":
+            out["nccl_allreduce_in_graph"] = res
+        else:
+            out.update(res)
+            out["exchange"] = ("none (one GPU)" if world == 1 else
+                               "fused into K7: peer-memory stores + per-reaction flags over NVLink (tsd_exchange_t)")
+    return out
 
 
 def full_trajectory(runner, flush_buf):
@@ -500,11 +512,9 @@ def run_ours(args):
     data_dev = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
 
     # ---- device-resident throughput: inputs in HBM, one replayed CUDA graph per Langevin step
-    reduce = None
-    if ensemble_mode and world > 1:
-        import torch.distributed as dist
-        reduce = lambda t: dist.all_reduce(t, group=group)  # noqa: E731
-    eng, runner = build_runner(args, models, data_dev, reduce=reduce, ensemble_size=args.members if reduce else None)
+    fused = ensemble_mode and world > 1
+    eng, runner = build_runner(args, models, data_dev, ensemble_size=args.members if fused else None,
+                               exchange_group=group if fused else None)
     c0 = lib.tsd_launch_count()
     runner.use_graph, saved = False, runner.use_graph
     runner._one_step()  # eager step: counts our kernel launches per Langevin step

@@ -290,6 +290,23 @@ typedef struct {
   const int32_t* inv_index; /* (E) or NULL: score of edge e = inv[inv_index[e]] (edges->edge_upair) */
 } tsd_score_channel_t;
 
+/* One-shot exchange of the per-atom partial scores between the ranks of an ensemble whose members live on
+ * different GPUs (BASELINE config 3; the reference averages edge_inv over the members every step,
+ * models/sampler.py:96-111, and eq_transform is linear in edge_inv).  Fused into tsd_ld_step: the CTA of reaction g
+ * computes this rank's partial scores, STORES them into every peer's buffer over NVLink (peer-mapped memory),
+ * publishes a per-reaction flag (release, system scope), spins on its own flags until every rank's contribution
+ * of this step has arrived (acquire), sums the contributions in RANK ORDER (identical on all ranks, so positions
+ * stay bit-equal without a broadcast) and goes on with the update.  Double buffered by step parity; flag values are
+ * *epoch_base + step + 1, so buffers are never reset while a peer may still write them. */
+#define TSD_MAX_EXCHANGE_RANKS 8
+typedef struct {
+  int32_t world, rank;
+  int32_t num_graphs;                            /* G */
+  float* peer_data[TSD_MAX_EXCHANGE_RANKS];      /* rank p's buffer (2, world, N, 3); peer_data[rank] is local */
+  int32_t* peer_flags[TSD_MAX_EXCHANGE_RANKS];   /* rank p's flags (2, world, G), zero-initialised once */
+  const int32_t* epoch_base;                     /* (1) device: bumped by the caller before every new trajectory */
+} tsd_exchange_t;
+
 typedef struct {
   const float* sched;      /* rule LD:   (num_steps, 4): step_size, sigma, noise_scale, use_channel1
                             * rule DDPM: (num_steps, 8): sqrt(at), sqrt(1/at), sqrt(1/at - 1), sqrt(atm1) beta_t,
@@ -316,6 +333,9 @@ typedef struct {
                             * ensemble-member-per-GPU mode, where every rank runs tsd_eq_transform on its own
                             * members' edge_inv and the (N,3) partial scores are summed across ranks first
                             * (eq_transform is linear in edge_inv, sampler.py:96-111,208-209). */
+  const tsd_exchange_t* exchange; /* HOST pointer or NULL.  When set, channel 0 holds THIS rank's members' sum and
+                            * inv_div the TOTAL ensemble size; the partial scores are exchanged inside the kernel (see
+                            * tsd_exchange_t).  nan_flag bit 1 is set if a peer's contribution did not arrive within ~5 s. */
 } tsd_ld_params_t;
 
 int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, float* pos,
@@ -330,6 +350,13 @@ int tsd_eq_transform(const tsd_batch_t* batch, const tsd_edges_t* edges, const f
 /* Philox4x32-10 + Box-Muller normals exactly as tsd_ld_step draws them: out (N,3). */
 int tsd_philox_normal(int32_t num_nodes, uint64_t seed, int32_t step, int64_t atom_offset,
                       float* out, tsd_stream_t stream);
+
+/* Peer-mapped device memory for tsd_exchange_t: cudaMalloc + zero fill + cudaIpcGetMemHandle on the owner,
+ * cudaIpcOpenMemHandle on the peers (the 64-byte handle travels through the caller's process group). */
+int tsd_peer_alloc(uint64_t bytes, void** ptr, unsigned char* handle64);
+int tsd_peer_open(const unsigned char* handle64, void** ptr);
+int tsd_peer_close(void* ptr);
+int tsd_peer_free(void* ptr);
 
 /* ---- post-sampling geometry metrics, fp64 like the reference's numpy / scipy code.
  * tsd_dmae (clustering.py:98-105 `calc_DMAE`): out[b] = sum over i < j of |dm_ref - dm_guess[b]| (mape: / dm_ref),

@@ -59,11 +59,21 @@ class ScoreChannel(C.Structure):
                 ("weight", C.c_float), ("inv_index", C.c_void_p)]
 
 
+MAX_EXCHANGE_RANKS = 8
+
+
+class Exchange(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("num_graphs", C.c_int32),
+                ("peer_data", C.c_void_p * MAX_EXCHANGE_RANKS), ("peer_flags", C.c_void_p * MAX_EXCHANGE_RANKS),
+                ("epoch_base", C.c_void_p)]
+
+
 class LdParams(C.Structure):
     _fields_ = [("sched", C.c_void_p), ("num_steps", C.c_int32), ("step_counter", C.c_void_p),
                 ("ticket", C.c_void_p), ("nan_flag", C.c_void_p), ("noise", C.c_void_p), ("seed", C.c_uint64),
                 ("atom_offset", C.c_int64), ("inv_div", C.c_float), ("clip_pos", C.c_float), ("traj", C.c_void_p),
-                ("traj_steps", C.c_int32), ("traj_base_step", C.c_int32), ("rule", C.c_int32), ("node_score", C.c_void_p)]
+                ("traj_steps", C.c_int32), ("traj_base_step", C.c_int32), ("rule", C.c_int32), ("node_score", C.c_void_p),
+                ("exchange", C.POINTER(Exchange))]
 
 
 RULE_LD, RULE_DDPM, RULE_DDPM_DUALENC, RULE_GENERALIZED = 0, 1, 2, 3
@@ -99,6 +109,10 @@ _SIGNATURES = {
                     C.POINTER(LdParams), _P],
     "tsd_eq_transform": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.c_float, _P, _P],
     "tsd_philox_normal": [C.c_int32, C.c_uint64, C.c_int32, C.c_int64, _P, _P],
+    "tsd_peer_alloc": [C.c_uint64, C.POINTER(C.c_void_p), _P],
+    "tsd_peer_open": [_P, C.POINTER(C.c_void_p)],
+    "tsd_peer_close": [_P],
+    "tsd_peer_free": [_P],
     "tsd_dmae": [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P],
     "tsd_dmae_pos": [C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P],
     "tsd_min_match_scratch": [C.c_int32, C.c_int32, _P, _P],

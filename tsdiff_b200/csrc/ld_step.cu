@@ -173,9 +173,63 @@ __device__ __forceinline__ float3 k7_node_sum(const tsd_edges_t& e, const float*
   return make_float3(__fadd_rn(ax, bx), __fadd_rn(ay, by), __fadd_rn(az, bz));
 }
 
+// ------------------------------------------------------------ one-shot score exchange between ensemble ranks
+__device__ __forceinline__ void k7_st_release_sys(int* addr, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int k7_ld_acquire_sys(const int* addr) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long k7_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Reaction g of this rank: push the partial scores in snew[3 n] to every rank's buffer, publish the flag, wait
+// for every rank's contribution of this step and leave their rank-ordered sum in snew.  All CTAs of all ranks are
+// co-resident (one small CTA per reaction), every CTA pushes before it waits, and the dependencies are per
+// reaction: no rank can wait on a kernel that has not been launched, and nobody overwrites a buffer its peer may
+// still be reading (a rank can get at most one step ahead of the slowest peer, hence two buffers).
+__device__ void k7_exchange(const tsd_exchange_t& ex, int g, int n0, int n, int num_nodes, int step, float* snew,
+                            int* nan_flag) {
+  const int parity = step & 1;
+  const int expect = *ex.epoch_base + step + 1;
+  const size_t slab = (size_t)num_nodes * 3;  // one (rank, parity) block of scores
+  for (int p = 0; p < ex.world; ++p) {        // push: coalesced stores straight into peer p's memory
+    float* dst = ex.peer_data[p] + ((size_t)parity * ex.world + ex.rank) * slab + (size_t)3 * n0;
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) __stcg(dst + i, snew[i]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < ex.world) {
+    const int p = threadIdx.x;
+    k7_st_release_sys(ex.peer_flags[p] + ((size_t)parity * ex.world + ex.rank) * ex.num_graphs + g, expect);
+    // wait for rank p's contribution to reaction g (its flag lives in OUR memory: a local spin)
+    const int* mine = ex.peer_flags[ex.rank] + ((size_t)parity * ex.world + p) * ex.num_graphs + g;
+    const unsigned long long t0 = k7_globaltimer();
+    while (k7_ld_acquire_sys(mine) != expect) {
+      if (k7_globaltimer() - t0 > 5000000000ull) {  // a peer died or was never launched: do not hang the GPU
+        atomicOr(nan_flag, 2);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const float* src = ex.peer_data[ex.rank] + (size_t)parity * ex.world * slab + (size_t)3 * n0;
+  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) {
+    float s = __ldcg(src + i);  // L2: the peers' stores never pass through this SM's L1
+    for (int r = 1; r < ex.world; ++r) s = __fadd_rn(s, __ldcg(src + (size_t)r * slab + i));
+    snew[i] = s;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, tsd_edges_t e, float* __restrict__ pos,
                                                                 tsd_score_channel_t ch0, tsd_score_channel_t ch1,
-                                                                tsd_ld_params_t ld, int smem_edge_cap) {
+                                                                tsd_ld_params_t ld, tsd_exchange_t ex, int smem_edge_cap) {
   extern __shared__ float k7_dyn[];
   __shared__ float spos[3 * TSD_MAX_GRAPH_NODES];
   __shared__ float snew[3 * TSD_MAX_GRAPH_NODES];
@@ -207,10 +261,24 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
       for (int k = threadIdx.x; k < count; k += blockDim.x) sm.in_local[k] = e.in_eid[e0 + k] - e0;
       __syncthreads();
     }
+    const bool exchanged = ex.world > 0;
+    if (exchanged) {
+      // this rank's partial scores -> snew, exchanged in place for the rank-ordered sum over the ensemble
+      for (int li = threadIdx.x; li < n; li += blockDim.x) {
+        const float3 part = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, n0 + li)
+                                   : tsd_node_score(ch0, e, spos, n0, n0 + li, ld.inv_div);
+        snew[3 * li] = part.x;
+        snew[3 * li + 1] = part.y;
+        snew[3 * li + 2] = part.z;
+      }
+      __syncthreads();
+      k7_exchange(ex, g, n0, n, b.num_nodes, step, snew, ld.nan_flag);
+    }
     for (int li = threadIdx.x; li < n; li += blockDim.x) {
       const int i = n0 + li;
       float3 eps;
-      if (external) eps = make_float3(ld.node_score[3 * (size_t)i], ld.node_score[3 * (size_t)i + 1], ld.node_score[3 * (size_t)i + 2]);
+      if (exchanged) eps = make_float3(snew[3 * li], snew[3 * li + 1], snew[3 * li + 2]);
+      else if (external) eps = make_float3(ld.node_score[3 * (size_t)i], ld.node_score[3 * (size_t)i + 1], ld.node_score[3 * (size_t)i + 2]);
       else eps = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, i) : tsd_node_score(ch0, e, spos, n0, i, ld.inv_div);
       eps = tsd_clip_norm(eps, ch0.clip);
       if (use1) {
@@ -303,6 +371,14 @@ extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, f
   TSD_REQUIRE(batch && edges && pos && ch0 && (ch0->inv || ld->node_score) && ld && ld->sched && ld->step_counter &&
               ld->ticket && ld->nan_flag);
   TSD_REQUIRE(!(ld->node_score && ch1 && ch1->inv));  // the reduced-score mode is single channel
+  tsd_exchange_t ex;
+  memset(&ex, 0, sizeof(ex));
+  if (ld->exchange) {
+    ex = *ld->exchange;
+    TSD_REQUIRE(ex.world >= 1 && ex.world <= TSD_MAX_EXCHANGE_RANKS && ex.rank >= 0 && ex.rank < ex.world && ex.epoch_base &&
+                ex.num_graphs == batch->num_graphs && ch0->inv && !ld->node_score && !(ch1 && ch1->inv));
+    for (int p = 0; p < ex.world; ++p) TSD_REQUIRE(ex.peer_data[p] && ex.peer_flags[p]);
+  }
   TSD_REQUIRE(batch->max_graph_nodes <= TSD_MAX_GRAPH_NODES);
   TSD_REQUIRE(ld->rule >= TSD_RULE_LD && ld->rule <= TSD_RULE_GENERALIZED);
   if (batch->num_graphs == 0) return TSD_OK;
@@ -321,7 +397,39 @@ extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, f
     smem = (size_t)bytes;
     if (smem > 40 * 1024) TSD_CUDA(cudaFuncSetAttribute(k_ld_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
-  k_ld_step<<<batch->num_graphs, threads, smem, tsd_cu(stream)>>>(*batch, *edges, pos, *ch0, ch1 ? *ch1 : off, *ld, cap);
+  k_ld_step<<<batch->num_graphs, threads, smem, tsd_cu(stream)>>>(*batch, *edges, pos, *ch0, ch1 ? *ch1 : off, *ld, ex, cap);
   TSD_LAUNCH_CHECK();
+  return TSD_OK;
+}
+
+// ------------------------------------------------------------------------- peer-mapped memory (CUDA IPC)
+extern "C" int tsd_peer_alloc(uint64_t bytes, void** ptr, unsigned char* handle64) {
+  TSD_REQUIRE(ptr && handle64 && bytes > 0);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  TSD_CUDA(cudaMalloc(ptr, bytes));
+  TSD_CUDA(cudaMemset(*ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  TSD_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle64, &h, 64);
+  return TSD_OK;
+}
+
+extern "C" int tsd_peer_open(const unsigned char* handle64, void** ptr) {
+  TSD_REQUIRE(ptr && handle64);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  TSD_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return TSD_OK;
+}
+
+extern "C" int tsd_peer_close(void* ptr) {
+  TSD_REQUIRE(ptr);
+  TSD_CUDA(cudaIpcCloseMemHandle(ptr));
+  return TSD_OK;
+}
+
+extern "C" int tsd_peer_free(void* ptr) {
+  TSD_REQUIRE(ptr);
+  TSD_CUDA(cudaFree(ptr));
   return TSD_OK;
 }

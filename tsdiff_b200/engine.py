@@ -553,17 +553,101 @@ class DualScoreEngine:
     num_members = 1
 
 
+class PeerExchange:
+    """Peer-mapped buffers of the one-shot score exchange fused into K7 (tsd_exchange_t): the ensemble-member-per-GPU
+    mode (BASELINE config 3).  Every rank of `group` owns a (2, world, N, 3) score buffer and (2, world, G) flags in
+    memory its peers can store into (CUDA IPC over NVLink); the 64-byte handles travel through the process group once.
+    `PeerExchange.local(plan, world)` wires `world` emulated ranks of ONE process / ONE device together instead (used
+    by the single-GPU protocol test: same kernel code, the "peers" are just other buffers)."""
+
+    def __init__(self, plan, group=None, _local=None):
+        import torch.distributed as dist
+        lib = L.load()
+        self.plan = plan
+        n, g = max(plan.num_nodes, 1), max(plan.num_graphs, 1)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=plan.device)
+        self._opened, self._owned = [], None
+        if _local is not None:
+            self.world, self.rank, bufs = _local
+            self._keep = bufs
+            ptrs = [(d.data_ptr(), f.data_ptr()) for d, f in bufs]
+        else:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            if self.world > L.MAX_EXCHANGE_RANKS:
+                raise L.TsdError("the fused score exchange supports up to %d ranks" % L.MAX_EXCHANGE_RANKS)
+            data_bytes = 2 * self.world * n * 3 * 4
+            data_bytes = (data_bytes + 255) // 256 * 256
+            total = data_bytes + 2 * self.world * g * 4
+            base, handle = C.c_void_p(), (C.c_ubyte * 64)()
+            with torch.cuda.device(plan.device):
+                L.check(lib.tsd_peer_alloc(total, C.byref(base), handle), "tsd_peer_alloc")
+                self._owned = base.value
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+                ptrs = []
+                for p in range(self.world):
+                    if p == self.rank:
+                        addr = base.value
+                    else:
+                        q = C.c_void_p()
+                        buf = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+                        L.check(lib.tsd_peer_open(buf, C.byref(q)), "tsd_peer_open")
+                        self._opened.append(q.value)
+                        addr = q.value
+                    ptrs.append((addr, addr + data_bytes))
+                dist.barrier(group=group)  # every rank has opened every buffer before anyone stores into them
+        self.c = L.Exchange()
+        self.c.world, self.c.rank, self.c.num_graphs = self.world, self.rank, plan.num_graphs
+        for p, (d, f) in enumerate(ptrs):
+            self.c.peer_data[p] = d
+            self.c.peer_flags[p] = f
+        self.c.epoch_base = self.epoch.data_ptr()
+
+    @classmethod
+    def local(cls, plans):
+        """One PeerExchange per emulated rank (plans[r] = that rank's BatchPlan, all on one device)."""
+        world = len(plans)
+        n, g = max(plans[0].num_nodes, 1), max(plans[0].num_graphs, 1)
+        dev = plans[0].device
+        bufs = [(torch.zeros(2 * world * n * 3, dtype=torch.float32, device=dev),
+                 torch.zeros(2 * world * g, dtype=torch.int32, device=dev)) for _ in range(world)]
+        return [cls(plans[r], _local=(world, r, bufs)) for r in range(world)]
+
+    def new_trajectory(self, n_steps):
+        """Flag values are epoch_base + step + 1: moving the base past the last trajectory's values makes its
+        leftovers (and those of a faster peer that already started the next one) unambiguous without any reset."""
+        self.epoch.add_(int(n_steps) + 1)
+
+    def close(self):
+        lib = L.load()
+        for q in self._opened:
+            lib.tsd_peer_close(C.c_void_p(q))
+        self._opened = []
+        if self._owned:
+            torch.cuda.synchronize(self.plan.device)
+            lib.tsd_peer_free(C.c_void_p(self._owned))
+            self._owned = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LangevinRunner:
     """Runs the Langevin loop for either engine: per step [K2, eps-net kernels, K7], captured
     once in a CUDA graph and replayed; per-step scalars come from a device table indexed by
     a device step counter (the score net ignores the time step)."""
 
     def __init__(self, engine, ch0, ch1, sched, pos, noise=None, seed=0, atom_offset=0, clip_pos=None,
-                 keep_traj=True, use_graph=True, rule=L.RULE_LD, reduce=None, ensemble_size=None):
+                 keep_traj=True, use_graph=True, rule=L.RULE_LD, reduce=None, ensemble_size=None, exchange=None):
         """reduce / ensemble_size: the ensemble-member-per-GPU mode.  `engine` holds this rank's members only;
         every step the rank's partial per-atom scores eq_transform(sum of local edge_inv / ensemble_size) are
         summed over the ranks by `reduce(tensor)` (in place, e.g. an NCCL all-reduce) before the update.  All
-        ranks hold the same positions and draw the same noise, so they stay in lockstep without a broadcast."""
+        ranks hold the same positions and draw the same noise, so they stay in lockstep without a broadcast.
+        exchange: a PeerExchange -- the same mode with the exchange FUSED into K7 (peer-memory stores + flags over
+        NVLink instead of a collective; no extra kernel, nothing but K7 in the step depends on the peers)."""
         assert sched.size(1) == (8 if rule in (L.RULE_DDPM, L.RULE_DDPM_DUALENC) else 4)
         self.engine, self.plan = engine, engine.plan
         dev = self.plan.device
@@ -582,9 +666,14 @@ class LangevinRunner:
         self.reduce = reduce
         self.node_eq = None
         inv_div = float(engine.num_members)
+        assert reduce is None or exchange is None
+        self.exchange = exchange
         if reduce is not None:
             assert ch1 is None and ensemble_size is not None and ensemble_size >= engine.num_members
             self.node_eq = torch.zeros(max(self.plan.num_nodes, 1), 3, dtype=torch.float32, device=dev)
+            inv_div = float(ensemble_size)
+        if exchange is not None:
+            assert ch1 is None and ensemble_size is not None and ensemble_size >= engine.num_members
             inv_div = float(ensemble_size)
         self.inv_div = inv_div
         self.ld = L.LdParams(
@@ -593,7 +682,8 @@ class LangevinRunner:
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(atom_offset), inv_div,
             float(clip_pos) if clip_pos is not None else 0.0,
             self.traj.data_ptr() if self.traj is not None else None, self.n_steps if keep_traj else 0, 0, int(rule),
-            self.node_eq.data_ptr() if self.node_eq is not None else None)
+            self.node_eq.data_ptr() if self.node_eq is not None else None,
+            C.pointer(exchange.c) if exchange is not None else None)
         self.use_graph = use_graph
         self.graph = None
 
@@ -610,6 +700,8 @@ class LangevinRunner:
                                 C.byref(self.ld), _stream()), "tsd_ld_step")
 
     def _reset(self):
+        if self.exchange is not None:
+            self.exchange.new_trajectory(self.n_steps)
         self.pos.copy_(self.pos0)
         self.step_counter.zero_()
         self.ticket.zero_()
@@ -644,10 +736,15 @@ class LangevinRunner:
             else:
                 self._one_step()
             if check_every and (k + 1) % check_every == 0 and int(self.nan_flag.item()):
-                raise FloatingPointError()
+                self._raise_flag()
         if int(self.nan_flag.item()):
-            raise FloatingPointError()
+            self._raise_flag()
         return self.pos
+
+    def _raise_flag(self):
+        if int(self.nan_flag.item()) & 2:
+            raise L.TsdError("score exchange: a peer's contribution did not arrive within 5 s (rank missing or stalled)")
+        raise FloatingPointError()
 
 
 def ddpm_schedule(betas, t_end, n_steps):

@@ -50,7 +50,9 @@ class EnsembleSampler(nn.Module):
         shard; use_graph=; ensemble_group= a torch.distributed process group whose ranks each hold a
         DIFFERENT subset of the ensemble members (`self.models`) and the SAME batch: the per-atom
         scores are all-reduced every step, which reproduces the reference's per-step mean over all
-        members (sampler.py:96-111) with one member per GPU (BASELINE config 3)."""
+        members (sampler.py:96-111) with one member per GPU (BASELINE config 3).  The exchange is fused into the
+        update kernel (peer-memory stores over NVLink, engine.PeerExchange); ensemble_exchange="nccl" selects an
+        NCCL all-reduce captured in the step graph instead."""
         from .. import _lib as L
         sampling_type = kwargs.get("sampling_type", "ddpm")
         if sampling_type not in ("ld", "ddpm"):
@@ -76,15 +78,18 @@ class EnsembleSampler(nn.Module):
         if sampling_type == "ddpm":
             sched, rule = E.ddpm_schedule(self.betas, t_end, n_steps), L.RULE_DDPM
         ch0, ch1 = eng.score_channels(clip)
-        reduce, ensemble_size = None, None
+        reduce, ensemble_size, exchange = None, None, None
         group = kwargs.get("ensemble_group")
         if group is not None:
             import torch.distributed as dist
             count = torch.tensor([len(self.models)], dtype=torch.int64, device=pos.device)
             dist.all_reduce(count, group=group)
             ensemble_size = int(count.item())
-            reduce = lambda t: dist.all_reduce(t, group=group)  # noqa: E731
-        runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, reduce=reduce, ensemble_size=ensemble_size,
+            if kwargs.get("ensemble_exchange", "fused") == "nccl" or dist.get_world_size(group) > L.MAX_EXCHANGE_RANKS:
+                reduce = lambda t: dist.all_reduce(t, group=group)  # noqa: E731
+            else:
+                exchange = E.PeerExchange(eng.plan, group)
+        runner = E.LangevinRunner(eng, ch0, ch1, sched, pos, reduce=reduce, ensemble_size=ensemble_size, exchange=exchange,
                                   noise=kwargs.get("noise"),
                                   seed=E.resolve_seed(kwargs.get("seed")),
                                   atom_offset=kwargs.get("atom_offset", 0), clip_pos=clip_pos,
@@ -92,4 +97,7 @@ class EnsembleSampler(nn.Module):
                                   rule=rule)
         pos = runner.run()
         traj = list(runner.traj.cpu().unbind(0)) if runner.traj is not None else []
+        if exchange is not None:
+            del runner
+            exchange.close()
         return pos, traj
