@@ -472,6 +472,57 @@ def measure_ensemble(args, rank, world, device, group, flush_buf, members=8):
     return out
 
 
+def measure_train_step(args, rank, world, device, group, steps=5, warmup=2):
+    """BASELINE config 4: training step forward + backward, batch 128 synthetic reactions per GPU, DDP gradient
+    all-reduce over NCCL when world > 1 (train.py:124-152: get_loss -> mean -> backward -> clip_grad_norm_ -> Adam).
+    fp32; CUDA-event timed, max over ranks."""
+    import torch.distributed as dist
+    from tsdiff_b200.synthetic import make_batch
+    from tsdiff_b200.training import allreduce_gradients
+    g = make_batch(128, seed=4000 + rank)
+    d = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in g.items()}
+    model = make_models(args, device, seed=0, math="fp32")[0]
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    pos = d["pos_init"] * 1.5
+    gen = torch.Generator(device=device).manual_seed(5 + rank)
+
+    def step():
+        opt.zero_grad()
+        half = torch.randint(0, model.num_timesteps, (g["num_graphs"] // 2 + 1,), device=device, generator=gen)
+        t = torch.cat([half, model.num_timesteps - 1 - half])[:g["num_graphs"]]
+        z = torch.randn(pos.shape, device=device, generator=gen)
+        loss = model.get_loss(d["atom_type"], d["r_feat"], d["p_feat"], pos, d["bond_index"], d["bond_type"], d["batch"],
+                              d["num_nodes_per_graph"], g["num_graphs"], time_step=t, pos_noise=z)
+        loss.mean().backward()
+        if world > 1:
+            allreduce_gradients(params, loss.size(0), group)
+        torch.nn.utils.clip_grad_norm_(params, 3000.0)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        loss = step()
+    t1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([t0.elapsed_time(t1) * 1e-3 / steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = float(t.item())
+    return {"what": "training step fwd+bwd+Adam, batch 128 reactions per GPU (BASELINE config 4), fp32 kernels",
+            "ms_per_step": t * 1e3, "reactions_per_s": world * 128 / t, "n_gpus": world, "steps": steps,
+            "atoms_per_gpu": int(g["atom_type"].numel()), "loss_mean": float(loss.mean()),
+            "gradient_allreduce": "none (one GPU)" if world == 1 else "atom-weighted NCCL all-reduce of one flat 11 MB bucket"}
+
+
 def full_trajectory(runner, flush_buf):
     """One full trajectory from the initial positions; returns device seconds (CUDA events)."""
     runner._reset()
@@ -576,6 +627,9 @@ def run_ours(args):
     if world > 1 and not ensemble_mode and args.members == 1 and args.network == "condensenc" and not args.no_extras:
         # BASELINE config 3 inside the driver's scaling run: 8 members, one (or 8 / N) per GPU, same batch
         ens_extra = measure_ensemble(args, rank, world, device, group, flush)
+    train_extra = None
+    if not ensemble_mode and args.members == 1 and args.network == "condensenc" and not args.no_extras:
+        train_extra = measure_train_step(args, rank, world, device, group)
     if rank != 0:
         return
     # ---- per-kernel rooflines (live, rank 0), secondary arms and the CPU baseline (N = 1 only)
@@ -643,6 +697,8 @@ def run_ours(args):
     out.update(extras)
     if ens_extra is not None:
         out["ensemble8"] = ens_extra
+    if train_extra is not None:
+        out["train_step"] = train_extra
     print(json.dumps(out), flush=True)
 
 

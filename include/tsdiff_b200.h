@@ -351,6 +351,52 @@ int tsd_eq_transform(const tsd_batch_t* batch, const tsd_edges_t* edges, const f
 int tsd_philox_normal(int32_t num_nodes, uint64_t seed, int32_t step, int64_t atom_offset,
                       float* out, tsd_stream_t stream);
 
+/* ---- training step (BASELINE config 4): the backward kernels behind
+ * `get_loss(...).mean().backward()` (models/epsnet/condensenc.py:267-328, train.py:124-152).  The training forward runs
+ * the operators above UNFUSED (pre-activations kept); tsdiff_b200/training.py wraps forward + backward of every operator
+ * in a torch.autograd.Function.  fp32, deterministic reductions (no float atomics).
+ *  tsd_act_forward / _backward       y = act(x);  dx = dy * act'(x)   (utils/activation_functions.py, schnet.py:65-71)
+ *  tsd_row_scale, tsd_cutoff_envelope  out[m,:] = x[m,:] * s[m], s = C(len) (schnet.py:91-98); own backward with dy
+ *  tsd_gate_rows                      out[m,:] = a[m,:] * table[(code[m] >> shift) & 0xffff, :] (edge.py:66-68);
+ *                                     a == NULL gathers the rows; backward w.r.t. a = the same op on dy
+ *  tsd_onehot                         (rows, classes) one-hot of the codes: d table = wgrad(onehot, dy * a)
+ *  tsd_transpose                      W (out,in) -> W^T, so the data gradient dx = dy W is tsd_linear with weight W^T
+ *  tsd_linear_wgrad                   dW (N,K) = dy^T x, db (N) = column sums of dy; dy (M,N), x (M,K); scratch floats
+ *                                     from tsd_linear_wgrad_scratch
+ *  tsd_cfconv_aggregate_backward      dx1, dfilt of agg_i = sum_{j->i} x1_j * filt_ji (schnet.py:102-107)
+ *  tsd_pair_features / _backward      cat[h_row * h_col, ea] (E, 2H) (common.py:226-229); dh (N, H)
+ *  tsd_eq_transform_backward          d inv of geometry.py:22-30 (mask as in tsd_score_channel_t)
+ *  tsd_condensed_node_embed_backward  d atom_embedding.weight (num_types, half), d atom_feat_embedding.weight (half, F)
+ *  tsd_sqerr_forward / _backward      loss[n] = sum_d (a - b)^2 (condensenc.py:324-326)
+ *  tsd_add, tsd_mul                   out = a + b (residual), out = a * b */
+int tsd_act_forward(int64_t n, const float* x, int32_t act, float* y, tsd_stream_t stream);
+int tsd_act_backward(int64_t n, const float* x, const float* dy, int32_t act, float* dx, tsd_stream_t stream);
+int tsd_row_scale(int32_t rows, int32_t H, const float* x, const float* s, float* out, tsd_stream_t stream);
+int tsd_cutoff_envelope(int32_t rows, const float* len, float cutoff, int32_t smooth, float* s, tsd_stream_t stream);
+int tsd_gate_rows(int32_t rows, int32_t H, const float* a, const float* table, const int32_t* code, int32_t shift,
+                  float* out, tsd_stream_t stream);
+int tsd_onehot(int32_t rows, int32_t classes, const int32_t* code, int32_t shift, float* out, tsd_stream_t stream);
+int tsd_transpose(int32_t rows, int32_t cols, const float* src, float* dst, tsd_stream_t stream);
+int tsd_linear_wgrad_scratch(int32_t M, int32_t N, int32_t K, uint64_t* floats);
+int tsd_linear_wgrad(int32_t M, int32_t N, int32_t K, const float* dy, const float* x, float* dW, float* db,
+                     float* scratch, tsd_stream_t stream);
+int tsd_cfconv_aggregate_backward(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t num_edges, int32_t H,
+                                  const float* x1, const float* filt, const float* dagg, float* dx1, float* dfilt,
+                                  tsd_stream_t stream);
+int tsd_pair_features(const tsd_edges_t* edges, int32_t num_edges, int32_t H, const float* h, const float* ea, float* out,
+                      tsd_stream_t stream);
+int tsd_pair_features_backward(const tsd_batch_t* batch, const tsd_edges_t* edges, int32_t H, const float* h,
+                               const float* dout, float* dh, tsd_stream_t stream);
+int tsd_eq_transform_backward(const tsd_edges_t* edges, int32_t num_edges, const float* pos, const int32_t* mask,
+                              int32_t mask_mode, float inv_div, const float* dnode, float* dinv, tsd_stream_t stream);
+int tsd_condensed_node_embed_backward(int32_t num_nodes, const int64_t* atom_type, const int64_t* r_feat,
+                                      const int64_t* p_feat, int32_t feat_dim, int32_t half, int32_t num_types,
+                                      const float* dz, float* d_atom_emb, float* d_feat_weight, tsd_stream_t stream);
+int tsd_sqerr_forward(int32_t n, const float* a, const float* b, float* loss, tsd_stream_t stream);
+int tsd_sqerr_backward(int32_t n, const float* a, const float* b, const float* dloss, float* da, tsd_stream_t stream);
+int tsd_add(int64_t n, const float* a, const float* b, float* out, tsd_stream_t stream);
+int tsd_mul(int64_t n, const float* a, const float* b, float* out, tsd_stream_t stream);
+
 /* Peer-mapped device memory for tsd_exchange_t: cudaMalloc + zero fill + cudaIpcGetMemHandle on the owner,
  * cudaIpcOpenMemHandle on the peers (the 64-byte handle travels through the caller's process group). */
 int tsd_peer_alloc(uint64_t bytes, void** ptr, unsigned char* handle64);

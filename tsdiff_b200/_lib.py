@@ -109,6 +109,24 @@ _SIGNATURES = {
                     C.POINTER(LdParams), _P],
     "tsd_eq_transform": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.c_float, _P, _P],
     "tsd_philox_normal": [C.c_int32, C.c_uint64, C.c_int32, C.c_int64, _P, _P],
+    "tsd_act_forward": [C.c_int64, _P, C.c_int32, _P, _P],
+    "tsd_act_backward": [C.c_int64, _P, _P, C.c_int32, _P, _P],
+    "tsd_row_scale": [C.c_int32, C.c_int32, _P, _P, _P, _P],
+    "tsd_cutoff_envelope": [C.c_int32, _P, C.c_float, C.c_int32, _P, _P],
+    "tsd_gate_rows": [C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P],
+    "tsd_onehot": [C.c_int32, C.c_int32, _P, C.c_int32, _P, _P],
+    "tsd_transpose": [C.c_int32, C.c_int32, _P, _P, _P],
+    "tsd_linear_wgrad_scratch": [C.c_int32, C.c_int32, C.c_int32, _P],
+    "tsd_linear_wgrad": [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P],
+    "tsd_cfconv_aggregate_backward": [C.POINTER(Batch), C.POINTER(Edges), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P],
+    "tsd_pair_features": [C.POINTER(Edges), C.c_int32, C.c_int32, _P, _P, _P, _P],
+    "tsd_pair_features_backward": [C.POINTER(Batch), C.POINTER(Edges), C.c_int32, _P, _P, _P, _P],
+    "tsd_eq_transform_backward": [C.POINTER(Edges), C.c_int32, _P, _P, C.c_int32, C.c_float, _P, _P, _P],
+    "tsd_condensed_node_embed_backward": [C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P],
+    "tsd_sqerr_forward": [C.c_int32, _P, _P, _P, _P],
+    "tsd_sqerr_backward": [C.c_int32, _P, _P, _P, _P, _P],
+    "tsd_add": [C.c_int64, _P, _P, _P, _P],
+    "tsd_mul": [C.c_int64, _P, _P, _P, _P],
     "tsd_peer_alloc": [C.c_uint64, C.POINTER(C.c_void_p), _P],
     "tsd_peer_open": [_P, C.POINTER(C.c_void_p)],
     "tsd_peer_close": [_P],

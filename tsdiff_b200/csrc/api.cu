@@ -34,6 +34,8 @@ static int tsd_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int
   return tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt, agg, s);
 }
 
+int tsd_linear_generic(int M, int N, int K, const float* x, const float* w, const float* b, float* out, cudaStream_t s);
+
 int tsd_launch_gine_aggregate(int num_nodes, int H, const int* in_ptr, const int* in_eid, const int* row,
                               const int* local_tab, const float* h, const float* ea, const float* eps, float* out,
                               cudaStream_t s);
@@ -265,6 +267,12 @@ extern "C" int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, 
 extern "C" int tsd_linear(int32_t rows, const int32_t* rows_dev, const float* x, const tsd_linear_t* lin, int32_t act,
                           float* out, int32_t math, tsd_stream_t stream) {
   TSD_REQUIRE(x && lin && lin->weight && out && rows >= 0);
+  if (lin->out_features % 64 != 0 || lin->in_features % 16 != 0) {
+    // odd shapes (K = 1 or 25, N = 1: edge MLP layer 0, the feature embedding, the last output layer and their data
+    // gradients in the training step): a plain fp32 kernel, one thread per output
+    TSD_REQUIRE(rows_dev == nullptr && act == TSD_ACT_NONE);
+    return tsd_linear_generic(rows, lin->out_features, lin->in_features, x, lin->weight, lin->bias, out, tsd_cu(stream));
+  }
   GemmArgs g = tsd_gemm_args();
   g.M_cap = rows;
   g.M_ptr = rows_dev;

@@ -59,21 +59,25 @@ class CondenseEncoderEpsNetwork(nn.Module):
     def get_loss(self, atom_type, r_feat, p_feat, pos, bond_index, bond_type, batch, num_nodes_per_graph=None,
                  num_graphs=None, anneal_power=2.0, extend_order=True, extend_radius=True, time_step=None,
                  pos_noise=None):
-        """condensenc.py:267-328, FORWARD VALUE ONLY (the validation loop of train.py:150-175 runs it
-        under torch.no_grad(); with gradients enabled it raises NotImplementedError: the backward kernels
-        are not built).  Per-atom loss (N,1).  Keyword-only extras: time_step (G,) and pos_noise (N,3)
-        replace the reference's torch.randint / torch.randn draws (:287-295)."""
-        E.require_no_grad(self, "CondenseEncoderEpsNetwork.get_loss")
+        """condensenc.py:267-328.  Per-atom loss (N,1).  With gradients enabled (train.py:124-152) the loss carries
+        the autograd graph over the parameters: forward and backward of every operator are kernels of the CUDA
+        library (tsdiff_b200/training.py, fp32).  Under torch.no_grad() (the validation loop, train.py:150-175) the
+        fused sampling kernels evaluate it.  Keyword-only extras: time_step (G,) and pos_noise (N,3) replace the
+        reference's torch.randint / torch.randn draws (:287-295)."""
+        dev = pos.device
+        if num_graphs is None:
+            num_graphs = int(batch.max().item()) + 1
+        if time_step is None:
+            t0, t1 = self.config.get("t0", 0), self.config.get("t1", self.num_timesteps)
+            half_1 = torch.randint(t0, t1, size=(num_graphs // 2 + 1,), device=dev)
+            time_step = torch.cat([half_1, t0 + t1 - 1 - half_1], dim=0)[:num_graphs]
+        if pos_noise is None:
+            pos_noise = torch.randn(size=pos.size(), device=dev)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from ... import training
+            return training.condensed_loss(self, atom_type, r_feat, p_feat, pos, bond_index, bond_type, batch, time_step,
+                                           pos_noise)
         with torch.no_grad():
-            dev = pos.device
-            if num_graphs is None:
-                num_graphs = int(batch.max().item()) + 1
-            if time_step is None:
-                t0, t1 = self.config.get("t0", 0), self.config.get("t1", self.num_timesteps)
-                half_1 = torch.randint(t0, t1, size=(num_graphs // 2 + 1,), device=dev)
-                time_step = torch.cat([half_1, t0 + t1 - 1 - half_1], dim=0)[:num_graphs]
-            if pos_noise is None:
-                pos_noise = torch.randn(size=pos.size(), device=dev)
             a = self.alphas.to(dev).index_select(0, time_step.to(dev))
             a_pos = a.index_select(0, batch).unsqueeze(-1)
             pos_perturbed = (pos + pos_noise.to(dev) * (1.0 - a_pos).sqrt() / a_pos.sqrt()).to(torch.float32).contiguous()
