@@ -274,12 +274,15 @@ int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float
  *         pos = center((mean + c6 noise) / c7)     (channel 0 only; every product / sum rounded)
  *   DDPM_DUALENC: pos0 = c0 pos - c1 (-eps); pos = center((c2 pos0 + c3 pos) / c4 + c5 noise)
  *   GENERALIZED:  pos = center(pos - (-eps) c0 + noise c1)
+ *   DSM:  the edge scores are multiplied by 1 / sigma[k] first (dualenc.py:305-309);
+ *         pos = center(pos + step_size[k] * eps + noise * noise_scale[k])      (sched columns as for LD)
  * noise: external tensor (n_steps, N, 3) if given, else Philox4x32-10 keyed by
  * (seed, step, atom_offset + atom) + Box-Muller.  mask mode: 0 all edges, 1 tab != 0, 2 tab == 0. */
 #define TSD_RULE_LD 0
 #define TSD_RULE_DDPM 1          /* EnsembleSampler `ddpm`, sampler.py:215-236 */
 #define TSD_RULE_DDPM_DUALENC 2  /* dualenc `ddpm_noisy` / `ddpm_det`, dualenc.py:906-944 */
 #define TSD_RULE_GENERALIZED 3   /* dualenc `generalized`, dualenc.py:872-904 */
+#define TSD_RULE_DSM 4           /* dualenc model type `dsm`, annealed Langevin dynamics, dualenc.py:1102-1203 */
 
 typedef struct {
   const float* inv;     /* (E) -- or (U) when inv_index is given -- or NULL to disable the channel */

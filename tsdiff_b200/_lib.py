@@ -76,7 +76,7 @@ class LdParams(C.Structure):
                 ("exchange", C.POINTER(Exchange))]
 
 
-RULE_LD, RULE_DDPM, RULE_DDPM_DUALENC, RULE_GENERALIZED = 0, 1, 2, 3
+RULE_LD, RULE_DDPM, RULE_DDPM_DUALENC, RULE_GENERALIZED, RULE_DSM = 0, 1, 2, 3, 4
 
 
 # symbol -> argtypes; every function returns int (0 = TSD_OK) unless listed in _RESTYPES

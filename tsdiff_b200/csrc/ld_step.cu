@@ -67,14 +67,14 @@ __device__ __forceinline__ bool tsd_edge_selected(const tsd_score_channel_t& ch,
 // score of atom `i` (global index): sum_{row=i} u*s - sum_{col=i} u*s, u = (p_row - p_col)/len.
 // spos holds the graph's positions (local index = global - n0).
 __device__ float3 tsd_node_score(const tsd_score_channel_t& ch, const tsd_edges_t& e, const float* spos, int n0, int i,
-                                 float inv_div) {
+                                 float inv_div, float inv_mul = 1.0f) {
   const float px = spos[3 * (i - n0)], py = spos[3 * (i - n0) + 1], pz = spos[3 * (i - n0) + 2];
   float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
   for (int k = e.row_ptr[i]; k < e.row_ptr[i + 1]; ++k) {
     if (!tsd_edge_selected(ch, k)) continue;
     int c = e.col[k] - n0;
     float inv_len = __fdiv_rn(1.0f, e.length[k]);
-    float s = __fdiv_rn(ch.inv[ch.inv_index ? ch.inv_index[k] : k], inv_div);
+    float s = __fdiv_rn(__fmul_rn(ch.inv[ch.inv_index ? ch.inv_index[k] : k], inv_mul), inv_div);
     ax = __fadd_rn(ax, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(px, spos[3 * c])), s));
     ay = __fadd_rn(ay, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(py, spos[3 * c + 1])), s));
     az = __fadd_rn(az, __fmul_rn(__fmul_rn(inv_len, __fsub_rn(pz, spos[3 * c + 2])), s));
@@ -84,7 +84,7 @@ __device__ float3 tsd_node_score(const tsd_score_channel_t& ch, const tsd_edges_
     if (!tsd_edge_selected(ch, id)) continue;
     int r = e.row[id] - n0;
     float inv_len = __fdiv_rn(1.0f, e.length[id]);
-    float s = __fdiv_rn(ch.inv[ch.inv_index ? ch.inv_index[id] : id], inv_div);
+    float s = __fdiv_rn(__fmul_rn(ch.inv[ch.inv_index ? ch.inv_index[id] : id], inv_mul), inv_div);
     bx = __fadd_rn(bx, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r], px)), s));
     by = __fadd_rn(by, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 1], py)), s));
     bz = __fadd_rn(bz, __fmul_rn(-__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 2], pz)), s));
@@ -138,14 +138,14 @@ struct LdSmem {
 };
 
 __device__ __forceinline__ void k7_edge_terms(const tsd_score_channel_t& ch, const tsd_edges_t& e, const float* spos,
-                                              int n0, int e0, int count, float inv_div, float* term) {
+                                              int n0, int e0, int count, float inv_div, float inv_mul, float* term) {
   for (int k = threadIdx.x; k < count; k += blockDim.x) {
     const int id = e0 + k;
     float tx = 0.f, ty = 0.f, tz = 0.f;
     if (tsd_edge_selected(ch, id)) {
       const int r = e.row[id] - n0, c = e.col[id] - n0;
       const float inv_len = __fdiv_rn(1.0f, e.length[id]);
-      const float s = __fdiv_rn(ch.inv[ch.inv_index ? ch.inv_index[id] : id], inv_div);
+      const float s = __fdiv_rn(__fmul_rn(ch.inv[ch.inv_index ? ch.inv_index[id] : id], inv_mul), inv_div);
       tx = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r], spos[3 * c])), s);
       ty = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 1], spos[3 * c + 1])), s);
       tz = __fmul_rn(__fmul_rn(inv_len, __fsub_rn(spos[3 * r + 2], spos[3 * c + 2])), s);
@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
     const float* sc = ld.sched + (size_t)(wide ? 8 : 4) * step;
     const float step_size = sc[0], sigma = sc[1], nscale = sc[2];
     const float use1_flag = rule == TSD_RULE_DDPM ? 0.f : (rule == TSD_RULE_DDPM_DUALENC ? sc[6] : sc[3]);
+    // DSM (dualenc.py:305-309,353-361): the edge scores are multiplied by 1 / sigma(noise level) before eq_transform
+    const float inv_mul = rule == TSD_RULE_DSM ? __fdiv_rn(1.0f, sigma) : 1.0f;
     const bool use1 = ch1.inv != nullptr && use1_flag != 0.f;
     const int e0 = e.row_ptr[n0], count = e.row_ptr[n0 + n] - e0;  // this graph's edges are contiguous
     const bool external = ld.node_score != nullptr;  // per-atom scores already reduced over the ensemble ranks
@@ -256,8 +258,8 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
     sm.term1 = k7_dyn + 3 * (size_t)smem_edge_cap;
     sm.in_local = reinterpret_cast<int*>(k7_dyn + (ch1.inv ? 6 : 3) * (size_t)smem_edge_cap);
     if (staged) {
-      k7_edge_terms(ch0, e, spos, n0, e0, count, ld.inv_div, sm.term0);
-      if (use1) k7_edge_terms(ch1, e, spos, n0, e0, count, ld.inv_div, sm.term1);
+      k7_edge_terms(ch0, e, spos, n0, e0, count, ld.inv_div, inv_mul, sm.term0);
+      if (use1) k7_edge_terms(ch1, e, spos, n0, e0, count, ld.inv_div, inv_mul, sm.term1);
       for (int k = threadIdx.x; k < count; k += blockDim.x) sm.in_local[k] = e.in_eid[e0 + k] - e0;
       __syncthreads();
     }
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
       // this rank's partial scores -> snew, exchanged in place for the rank-ordered sum over the ensemble
       for (int li = threadIdx.x; li < n; li += blockDim.x) {
         const float3 part = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, n0 + li)
-                                   : tsd_node_score(ch0, e, spos, n0, n0 + li, ld.inv_div);
+                                   : tsd_node_score(ch0, e, spos, n0, n0 + li, ld.inv_div, inv_mul);
         snew[3 * li] = part.x;
         snew[3 * li + 1] = part.y;
         snew[3 * li + 2] = part.z;
@@ -279,10 +281,10 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
       float3 eps;
       if (exchanged) eps = make_float3(snew[3 * li], snew[3 * li + 1], snew[3 * li + 2]);
       else if (external) eps = make_float3(ld.node_score[3 * (size_t)i], ld.node_score[3 * (size_t)i + 1], ld.node_score[3 * (size_t)i + 2]);
-      else eps = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, i) : tsd_node_score(ch0, e, spos, n0, i, ld.inv_div);
+      else eps = staged ? k7_node_sum(e, sm.term0, sm.in_local, e0, i) : tsd_node_score(ch0, e, spos, n0, i, ld.inv_div, inv_mul);
       eps = tsd_clip_norm(eps, ch0.clip);
       if (use1) {
-        float3 g1 = staged ? k7_node_sum(e, sm.term1, sm.in_local, e0, i) : tsd_node_score(ch1, e, spos, n0, i, ld.inv_div);
+        float3 g1 = staged ? k7_node_sum(e, sm.term1, sm.in_local, e0, i) : tsd_node_score(ch1, e, spos, n0, i, ld.inv_div, inv_mul);
         g1 = tsd_clip_norm(g1, ch1.clip);
         eps.x = __fadd_rn(eps.x, __fmul_rn(g1.x, ch1.weight));
         eps.y = __fadd_rn(eps.y, __fmul_rn(g1.y, ch1.weight));
@@ -308,6 +310,11 @@ __global__ void __launch_bounds__(TSD_MAX_GRAPH_NODES) k_ld_step(tsd_batch_t b, 
           out[d] = __fadd_rn(mean, __fmul_rn(sc[5], zv[d]));
         }
         nx = out[0], ny = out[1], nz = out[2];
+      } else if (rule == TSD_RULE_DSM) {
+        // dualenc.py:1183-1184: pos + step_size * eps_pos + randn * sqrt(2 step_size)
+        nx = __fadd_rn(__fadd_rn(spos[3 * li], __fmul_rn(step_size, eps.x)), __fmul_rn(z.x, nscale));
+        ny = __fadd_rn(__fadd_rn(spos[3 * li + 1], __fmul_rn(step_size, eps.y)), __fmul_rn(z.y, nscale));
+        nz = __fadd_rn(__fadd_rn(spos[3 * li + 2], __fmul_rn(step_size, eps.z)), __fmul_rn(z.z, nscale));
       } else if (rule == TSD_RULE_GENERALIZED) {
         // dualenc.py:904: pos - et * step_size_pos + noise * step_size_noise, et = -eps
         nx = __fadd_rn(__fsub_rn(spos[3 * li], __fmul_rn(-eps.x, sc[0])), __fmul_rn(z.x, sc[1]));
@@ -380,7 +387,7 @@ extern "C" int tsd_ld_step(const tsd_batch_t* batch, const tsd_edges_t* edges, f
     for (int p = 0; p < ex.world; ++p) TSD_REQUIRE(ex.peer_data[p] && ex.peer_flags[p]);
   }
   TSD_REQUIRE(batch->max_graph_nodes <= TSD_MAX_GRAPH_NODES);
-  TSD_REQUIRE(ld->rule >= TSD_RULE_LD && ld->rule <= TSD_RULE_GENERALIZED);
+  TSD_REQUIRE(ld->rule >= TSD_RULE_LD && ld->rule <= TSD_RULE_DSM);
   if (batch->num_graphs == 0) return TSD_OK;
   tsd_score_channel_t off;
   memset(&off, 0, sizeof(off));

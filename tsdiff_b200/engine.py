@@ -447,7 +447,7 @@ class DualScoreEngine:
     """Path A: DualEncoderEpsNetwork evaluation (models/epsnet/dualenc.py:206-374, type
     'diffusion').  Global SchNet on all edges, local GIN on edges with type > 0."""
 
-    def __init__(self, model, atom_type, bond_index, bond_type, batch, math="fp32"):
+    def __init__(self, model, atom_type, bond_index, bond_type, batch, math="fp32", extend_order=True, extend_radius=True):
         lib = L.load()
         cfg = model.config
         self.model, self.cfg = model, cfg
@@ -455,11 +455,14 @@ class DualScoreEngine:
         _require_cuda(atom_type, "atom_type")
         _require_cuda(batch, "batch")
         self.ts = bool(getattr(model, "TS", False))
-        self.plan = BatchPlan(1, batch, bond_index, bond_type, int(cfg.edge_order), 0, ts_decode=self.ts, upairs=True)
+        # common.py:387-417: extend_order=False keeps the bonds as they are (= hop order 1), extend_radius=False adds no
+        # radius edges (a build cutoff of 0: d^2 < 0 never holds); CFConv keeps config.cutoff for its envelope
+        self.plan = BatchPlan(1, batch, bond_index, bond_type, int(cfg.edge_order) if extend_order else 1, 0,
+                              ts_decode=self.ts, upairs=True)
         plan = self.plan
         h = int(cfg.hidden_dim)
         self.hidden = h
-        self.cutoff = float(cfg.cutoff)
+        self.cutoff = float(cfg.cutoff) if extend_radius else 0.0
         self.ws = _Scratch(plan, h, 7, 7, 1, math)
         self.side = torch.cuda.Stream(device=plan.device)  # the local (GIN) branch runs beside the global one
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
@@ -648,7 +651,7 @@ class LangevinRunner:
         ranks hold the same positions and draw the same noise, so they stay in lockstep without a broadcast.
         exchange: a PeerExchange -- the same mode with the exchange FUSED into K7 (peer-memory stores + flags over
         NVLink instead of a collective; no extra kernel, nothing but K7 in the step depends on the peers)."""
-        assert sched.size(1) == (8 if rule in (L.RULE_DDPM, L.RULE_DDPM_DUALENC) else 4)
+        assert sched.dim() == 2 and sched.size(1) == (8 if rule in (L.RULE_DDPM, L.RULE_DDPM_DUALENC) else 4)
         self.engine, self.plan = engine, engine.plan
         dev = self.plan.device
         self.n_steps = sched.size(0)
@@ -806,6 +809,23 @@ def dualenc_branch_schedule(alphas, betas, n_steps, step_lr, sampling_type, eta=
                                    (1 - beta_t).sqrt() * (1 - atm1), 1.0 - at, mask * torch.exp(0.5 * logvar),
                                    use_global, torch.zeros(1)]))
     return torch.stack(rows).contiguous().float()
+
+
+def dsm_schedule(sigmas, n_steps, step_lr, min_sigma=0, global_start_sigma=float("inf")):
+    """(levels * n_steps, 4) table [step_size, sigma, sqrt(2 step_size), use_global] of the annealed Langevin loop of
+    dualenc.py:1102-1203: for every noise level sigma >= min_sigma (in order; the loop breaks at the first smaller one)
+    n_steps rows with step_size = step_lr * (sigma / sigmas[-1]) ** 2, in the reference's fp32 tensor arithmetic."""
+    sigmas = sigmas.detach().float().cpu()
+    rows = []
+    for sigma in sigmas:
+        if sigma < min_sigma:
+            break
+        step_size = step_lr * (sigma / sigmas[-1]) ** 2
+        row = torch.stack([step_size, sigma, torch.sqrt(step_size * 2), (sigma < global_start_sigma).float()])
+        rows.extend([row] * int(n_steps))
+    if not rows:
+        return torch.zeros(0, 4)
+    return torch.stack(rows).contiguous()
 
 
 def ld_schedule(alphas, n_steps, step_lr, global_start_sigma=float("inf")):
