@@ -623,6 +623,11 @@ def run_ours(args):
                "includes": "H2D inputs, bond-order tables, graph capture, %d LD steps, D2H trajectory+positions"
                            % args.ld_steps}
 
+    if runner.exchange is not None:  # collective: every rank unmaps its peers before anyone frees
+        ex, runner.ld.exchange = runner.exchange, None
+        runner.graph = None
+        ex.close()
+        runner.exchange = None
     ens_extra = None
     if world > 1 and not ensemble_mode and args.members == 1 and args.network == "condensenc" and not args.no_extras:
         # BASELINE config 3 inside the driver's scaling run: 8 members, one (or 8 / N) per GPU, same batch
@@ -633,8 +638,9 @@ def run_ours(args):
     if rank != 0:
         return
     # ---- per-kernel rooflines (live, rank 0), secondary arms and the CPU baseline (N = 1 only)
-    runner._reset()
-    runner.run(n_steps=min(args.ld_steps, 2000))  # a late-trajectory edge list (every pair inside the cutoff)
+    if not ensemble_mode:
+        runner._reset()
+        runner.run(n_steps=min(args.ld_steps, 2000))  # a late-trajectory edge list (every pair inside the cutoff)
     mean_edges = eng.plan.edge_count()
     work_rows = eng.plan.work_count()
     tensor_roof, hbm_roof = kernel_rooflines(args, eng, peaks, device)

@@ -69,7 +69,7 @@ def test_no_cpu_fallback():
     with pytest.raises(L.TsdError):
         m(g["atom_type"], g["r_feat"], g["p_feat"], g["pos_init"], g["bond_index"], g["bond_type"], g["batch"], None)
     args = (g["atom_type"], g["r_feat"], g["p_feat"], g["pos_init"], g["bond_index"], g["bond_type"], g["batch"])
-    with pytest.raises(NotImplementedError):  # gradients enabled: the backward kernels are not built
+    with pytest.raises(L.TsdError):  # gradients enabled: the training kernels are CUDA only as well
         m.get_loss(*args)
     with torch.no_grad(), pytest.raises(L.TsdError):  # forward value needs the CUDA path too
         m.get_loss(*args)

@@ -24,12 +24,7 @@ int tsd_launch_cfconv_aggregate_staged(const tsd_batch_t* b, int H, const int* i
 // The switch uses the host-side edge capacity (the valid count lives on the device).
 static int tsd_aggregate(const tsd_batch_t* batch, const tsd_edges_t* edges, int H, const float* x1, const float* filt,
                          float* agg, cudaStream_t s) {
-  static int forced = -2;
-  if (forced == -2) {
-    const char* v = getenv("TSD_AGG_VARIANT");
-    forced = v ? atoi(v) : -1;
-  }
-  const bool staged = forced == 5 || (forced < 0 && batch->edge_capacity >= (1 << 18) && batch->max_graph_nodes <= 256);
+  const bool staged = batch->edge_capacity >= (1 << 18) && batch->max_graph_nodes <= 256;
   if (staged) return tsd_launch_cfconv_aggregate_staged(batch, H, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt, agg, s);
   return tsd_launch_cfconv_aggregate(batch->num_nodes, H, edges->in_ptr, edges->in_eid, edges->in_src, x1, filt, agg, s);
 }
@@ -498,10 +493,6 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
   }
   bool split = nf_pool && nf_pool_count >= 2 && num_blocks >= 2;
   for (int l = 0; l + 1 < num_blocks && split; ++l) split = blocks[l].fused_w && blocks[l].fused_b;
-  {
-    const char* e = getenv("TSD_ENCODER_SPLIT");
-    if (e && e[0] == '0') split = false;
-  }
   const size_t node_elems = (size_t)batch->num_nodes * H;
   float* aggbuf[2] = {nf1, split ? nf2 : nf1};
   float* xh[2] = {nf_pool, split ? nf_pool + node_elems : nullptr};

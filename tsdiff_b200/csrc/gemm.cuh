@@ -52,7 +52,6 @@ struct GemmArgs {
   float* out_vec;
   int accumulate;
   int round_out;           // tf32 mode: round stored outputs to TF32 (RNE) because a tensor-core GEMM consumes them
-  unsigned long long* dbg;  // optional timeline buffer (TSD_GEMM_DBG=1), CTA 0 writes globaltimer stamps
 };
 
 static inline GemmArgs tsd_gemm_args() {
@@ -139,7 +138,6 @@ struct ChainArgs {
   const float* A;         // (M_cap, H) dense input of stage 0
   int num_stages;         // 2 or 3
   ChainStage st[3];
-  unsigned long long* dbg;  // optional CTA-0 timeline (TSD_GEMM_DBG=1)
 };
 
 // node side of an interaction block for few rows: fused aggregation + transposed chained linears (node_update.cu)

@@ -189,7 +189,6 @@ __device__ __forceinline__ void chain_stage_run(const ChainArgs& p, const ChainM
   __syncwarp();
   mbar_wait(&c.bar_accum[STAGE], 0);
   tc_fence_after();
-  if (c.tid == 0) TC_STAMP(1 + 2 * STAGE);
   if (!last && !via_tile && c.warp == 0 && c.lane == 0) {
     // every ring slot is free now (this stage's MMAs retired) and this epilogue does not need
     // the ring as a transpose tile: start the next stage's weights so they land meanwhile
@@ -205,7 +204,6 @@ __device__ __forceinline__ void chain_stage_run(const ChainArgs& p, const ChainM
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (c.tid == 0) TC_STAMP(2 + 2 * STAGE);
 }
 
 template <int KIND>
@@ -218,7 +216,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chain_tf32(const ChainArgs p,
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[256];  // bias of the stage in flight (224 KiB + this must stay < 227 KiB)
 
-  if (threadIdx.x == 0) TC_STAMP(0);
   ChainCtx c;
   c.tid = threadIdx.x, c.warp = c.tid >> 5, c.lane = c.tid & 31;
   // predecessor-independent setup first (see launch_pdl): barriers and descriptor prefetch
@@ -321,29 +318,10 @@ int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream) {
   if (ring_bytes < tile_bytes) ring_bytes = tile_bytes;
   const size_t smem = (size_t)num_kb * TC_A_PANEL_BYTES + ring_bytes + 1024;
   const int tmem_cols = 2 * c.H;  // 512 or 256: both powers of two
-  static unsigned long long* dbg = nullptr;
-  static bool dbg_checked = false;
-  if (!dbg_checked) {
-    dbg_checked = true;
-    const char* e = getenv("TSD_GEMM_DBG");
-    if (e && e[0] == '1') cudaMalloc(&dbg, 64 * sizeof(unsigned long long));
-  }
-  ChainArgs cc = c;
-  cc.dbg = dbg;
-  if (dbg) cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), stream);
   int rc = TSD_ERR_UNSUPPORTED;
   const int kind = chain_matches(c, CH_FILTER) ? CH_FILTER : chain_matches(c, CH_NODE3) ? CH_NODE3 : chain_matches(c, CH_NODE2) ? CH_NODE2 : -1;
-  if (kind == CH_FILTER) rc = chain_launch<CH_FILTER>(cc, maps, tmem_cols, smem, stream);
-  else if (kind == CH_NODE3) rc = chain_launch<CH_NODE3>(cc, maps, tmem_cols, smem, stream);
-  else if (kind == CH_NODE2) rc = chain_launch<CH_NODE2>(cc, maps, tmem_cols, smem, stream);
-  if (rc != TSD_OK) return rc;
-  if (dbg) {
-    unsigned long long hb[64];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(hb, dbg, sizeof(hb), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[chain dbg] M_cap=%d H=%d stages=%d |", c.M_cap, c.H, c.num_stages);
-    for (int i = 1; i <= 2 * c.num_stages; ++i) fprintf(stderr, " %s%llu", (i & 1) ? "acc " : "epi ", hb[i] - hb[0]);
-    fprintf(stderr, "\n");
-  }
-  return TSD_OK;
+  if (kind == CH_FILTER) rc = chain_launch<CH_FILTER>(c, maps, tmem_cols, smem, stream);
+  else if (kind == CH_NODE3) rc = chain_launch<CH_NODE3>(c, maps, tmem_cols, smem, stream);
+  else if (kind == CH_NODE2) rc = chain_launch<CH_NODE2>(c, maps, tmem_cols, smem, stream);
+  return rc;
 }

@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
   __shared__ float s_dot[NSL - 1][TC_BM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) TC_STAMP(0);
   constexpr bool dense_a = AKIND == TSD_A_PLAIN;
   // predecessor-independent setup first (see launch_pdl): barriers and descriptor prefetch
   if (tid == 0) {
@@ -130,7 +129,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
   const int m0 = blockIdx.x * TC_BM;
   if (m0 >= M) return;  // uniform across the CTA, before any allocation
   const int N = p.N, K = p.K;
-  if (tid == 0) TC_STAMP(1);
   const uint32_t b_panel_bytes = (uint32_t)N * TC_BK * 4;
   const uint32_t stage_bytes = TC_A_PANEL_BYTES + b_panel_bytes;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -147,7 +145,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const int num_kb = K / TC_BK;
-  if (tid == 0) TC_STAMP(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -169,7 +166,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % TC_STAGES, round = kb / TC_STAGES;
         mbar_wait(&bar_full[s], (uint32_t)(round & 1));
-        if (kb < 8) TC_STAMP(8 + kb);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_base + (uint32_t)s * stage_bytes);
         const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)s * stage_bytes + TC_A_PANEL_BYTES);
@@ -179,7 +175,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
         umma_commit(&bar_empty[s]);
         if (kb == num_kb - 1) umma_commit(&bar_accum);
       }
-      TC_STAMP(3);
     }
   } else if (warp >= 2 && !dense_a) {
     // ------------------------------------------------------------ A producers (computed operand)
@@ -224,7 +219,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
   // the MUFU latency -- 2.1 us per 32-column chunk in the globaltimer timeline, now 0.4-1.0.)
   mbar_wait(&bar_accum, 0);
   tc_fence_after();
-  if (tid == 0) TC_STAMP(4);
   const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter of this warp, column half
   const int row = q * 32 + lane, m = m0 + row;
   const bool live = m < M;
@@ -240,7 +234,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
     const int c0 = half * cols_per_half + cc;
     uint32_t v[32];
     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-    if (tid == 0 && cc == 0) TC_STAMP(16);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -264,7 +257,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
         *reinterpret_cast<float4*>(tile + lane * TLD + j) = o;
       }
     }
-    if (tid == 0 && cc == 0) TC_STAMP(17);
     if (EPI != TSD_EPI_DOT) {
       __syncwarp();
       const int cg = (lane & 7) << 2;  // 8 lanes cover the 32 columns of one row: a full 128-byte line
@@ -286,7 +278,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
       }
       __syncwarp();
     }
-    if (tid == 0 && cc < 128) TC_STAMP(18 + (cc >> 5));
   }
   if (EPI == TSD_EPI_DOT) {
     if (half > 0) s_dot[half - 1][row] = dot;
@@ -299,25 +290,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
       p.out_vec[m] = p.accumulate ? p.out_vec[m] + r : r;
     }
   }
-  if (tid == 0) TC_STAMP(5);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) TC_STAMP(6);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols)
                  : "memory");
   }
-}
-
-unsigned long long* tc_dbg_buffer() {
-  static unsigned long long* buf = nullptr;
-  static bool checked = false;
-  if (!checked) {
-    checked = true;
-    const char* e = getenv("TSD_GEMM_DBG");
-    if (e && e[0] == '1') cudaMalloc(&buf, 64 * sizeof(unsigned long long));
-  }
-  return buf;
 }
 
 template <int ACT, int EPI, int AKIND, int NT>
@@ -331,43 +309,18 @@ int tc_launch_nt(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorM
   smem = (size_t)tc_stages(NT) * (TC_A_PANEL_BYTES + (size_t)g0.N * TC_BK * 4) + 1024;
   const size_t tiles = (size_t)(NT / 32) * 32 * 36 * sizeof(float) + 1024;  // epilogue transpose tiles reuse the pipeline
   if (smem < tiles) smem = tiles;
-  GemmArgs g = g0;
-  g.dbg = tc_dbg_buffer();
-  if (g.dbg) {
-    cudaMemsetAsync(g.dbg, 0, 64 * sizeof(unsigned long long), stream);
-  }
-  TSD_CUDA(launch_pdl(k_gemm_tf32<ACT, EPI, AKIND, NT>, dim3(tsd_ceil_div(g.M_cap, TC_BM)), dim3(NT), smem, stream, g,
+  TSD_CUDA(launch_pdl(k_gemm_tf32<ACT, EPI, AKIND, NT>, dim3(tsd_ceil_div(g0.M_cap, TC_BM)), dim3(NT), smem, stream, g0,
                       tmem_cols, map_a, map_w));
   TSD_LAUNCH_CHECK();
-  if (g.dbg) {
-    unsigned long long hb[64];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(hb, g.dbg, sizeof(hb), cudaMemcpyDeviceToHost);
-    unsigned long long* dbgv = hb;
-    unsigned long long t0 = dbgv[0];
-    fprintf(stderr, "[tc dbg] act=%d epi=%d akind=%d M_cap=%d N=%d K=%d | setup %llu alloc %llu | mma_done %llu accum %llu epi %llu end %llu | full:",
-            ACT, EPI, AKIND, g.M_cap, g.N, g.K, dbgv[1] - t0, dbgv[2] - t0, dbgv[3] - t0, dbgv[4] - t0, dbgv[5] - t0,
-            dbgv[6] - t0);
-    for (int i = 0; i < 8; ++i) fprintf(stderr, " %llu", dbgv[8 + i] ? dbgv[8 + i] - t0 : 0ull);
-    fprintf(stderr, " | epi-detail:");
-    for (int i = 16; i < 22; ++i) fprintf(stderr, " %llu", dbgv[i] ? dbgv[i] - t0 : 0ull);
-    fprintf(stderr, "\n");
-  }
   return TSD_OK;
 }
 
 // 512-thread CTAs when the tiles cannot fill the GPU at two per SM anyway (and every epilogue warp still
-// gets a whole 32-column chunk); TSD_GEMM_THREADS=256/512 forces a shape
+// gets a whole 32-column chunk)
 template <int ACT, int EPI, int AKIND>
 int tc_launch(const GemmArgs& g, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
               cudaStream_t stream) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("TSD_GEMM_THREADS");
-    forced = e ? atoi(e) : 0;
-  }
-  const bool wide_ok = g.N >= 128;
-  const bool wide = wide_ok && (forced == 512 || (forced != 256 && tsd_ceil_div(g.M_cap, TC_BM) <= 148));
+  const bool wide = g.N >= 128 && tsd_ceil_div(g.M_cap, TC_BM) <= 148;
   if (wide) return tc_launch_nt<ACT, EPI, AKIND, 512>(g, tmem_cols, smem, map_a, map_w, stream);
   return tc_launch_nt<ACT, EPI, AKIND, 256>(g, tmem_cols, smem, map_a, map_w, stream);
 }

@@ -158,27 +158,8 @@ int tsd_launch_cfconv_aggregate(int num_nodes, int H, const int* in_ptr, const i
   if (num_nodes == 0) return TSD_OK;
   const int slabs = tsd_ceil_div(H, 128);
   const long long warps = (long long)num_nodes * slabs;
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("TSD_AGG_VARIANT");
-    variant = e ? atoi(e) : 2;  // measured best at batch 100: UNROLL 4, 60 registers, 256 threads
-  }
-  switch (variant) {
-    case 1:
-      k_cfconv_aggregate<4><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
-      break;
-    case 2:
-      k_cfconv_aggregate<4><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
-      break;
-    case 3:
-      k_cfconv_aggregate<8><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
-      break;
-    case 4:
-      k_cfconv_aggregate<16><<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
-      break;
-    default:
-      k_cfconv_aggregate<8><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
-  }
+  // measured best at batch 100 (profiles/r1_aggregate_hbm.txt): UNROLL 4, 60 registers, 256 threads
+  k_cfconv_aggregate<4><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(num_nodes, H, slabs, in_ptr, in_eid, in_src, x1, filt, agg);
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }

@@ -132,8 +132,7 @@ class BatchPlan:
         # ---- undirected pair list: the per-edge networks run once per unordered pair (the two directions
         # of an edge have bit-identical length and, for symmetric pair tables, types)
         self.upair_capacity = int((counts_h * (counts_h - 1)).sum()) // 2 if g else 0
-        import os
-        self.upairs = bool(upairs) and os.environ.get("TSD_UPAIRS", "1") != "0" and self._tables_symmetric()
+        self.upairs = bool(upairs) and self._tables_symmetric()
         fields = [self.num_edges, self.row, self.col, self.length, self.tab0, self.tab1, self.in_b, self.row_ptr,
                   self.in_ptr, self.in_eid, self.in_src, self.graph_count]
         if self.upairs:
@@ -569,7 +568,7 @@ class PeerExchange:
         self.plan = plan
         n, g = max(plan.num_nodes, 1), max(plan.num_graphs, 1)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=plan.device)
-        self._opened, self._owned = [], None
+        self._opened, self._owned, self._group = [], None, group
         if _local is not None:
             self.world, self.rank, bufs = _local
             self._keep = bufs
@@ -622,21 +621,21 @@ class PeerExchange:
         self.epoch.add_(int(n_steps) + 1)
 
     def close(self):
+        """Collective over the group: every rank unmaps its peers' buffers, and only when ALL ranks have done so does
+        anyone free its own (an exporter must not free memory a peer still has mapped)."""
         lib = L.load()
+        if self._owned is None and not self._opened:
+            return
+        torch.cuda.synchronize(self.plan.device)
         for q in self._opened:
             lib.tsd_peer_close(C.c_void_p(q))
         self._opened = []
         if self._owned:
-            torch.cuda.synchronize(self.plan.device)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier(group=self._group)
             lib.tsd_peer_free(C.c_void_p(self._owned))
             self._owned = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
 
 class LangevinRunner:
     """Runs the Langevin loop for either engine: per step [K2, eps-net kernels, K7], captured
