@@ -519,7 +519,7 @@ def measure_train_step(args, rank, world, device, group, steps=5, warmup=2):
     t = float(t.item())
     return {"what": "training step fwd+bwd+Adam, batch 128 reactions per GPU (BASELINE config 4), fp32 kernels",
             "ms_per_step": t * 1e3, "reactions_per_s": world * 128 / t, "n_gpus": world, "steps": steps,
-            "atoms_per_gpu": int(g["atom_type"].numel()), "loss_mean": float(loss.mean()),
+            "atoms_per_gpu": int(g["atom_type"].numel()), "loss_mean": float(loss.detach().mean()),
             "gradient_allreduce": "none (one GPU)" if world == 1 else "atom-weighted NCCL all-reduce of one flat 11 MB bucket"}
 
 

@@ -19,14 +19,14 @@ def oracle_params(model):
 
 
 def rel_err(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp(min=1e-30))
 
 
 def max_rel_err(a, b):
     """Worst element error relative to the RMS magnitude of the reference vector.  (A plain
     element-wise |a-b|/|b| is ill-conditioned for the few edge scores that pass through 0.)"""
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.pow(2).mean().sqrt().clamp(min=1e-30))
 
 

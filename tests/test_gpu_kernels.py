@@ -567,14 +567,12 @@ def test_rigid_motion_invariance_batch100():
 @pytest.mark.parametrize("name", ["syn4", "rxn0"])
 def test_get_loss_forward_vs_reference_golden(name, golden_loss, rxn0, syn4):
     """get_loss forward values (the validation loss of train.py) of both networks against the reference's own
-    get_loss with the same time steps and noise; with gradients enabled the call refuses (no backward kernels)."""
+    get_loss with the same time steps and noise (path B with gradients: tests/test_gpu_training.py; path A with
+    gradients enabled refuses: its backward is not built)."""
     g = graph_for(name, rxn0, syn4)
     d = to_dev(g, DEV)
     ref = golden_loss["b_" + name]
     mb = make_model("condensenc", 0, DEV)
-    with pytest.raises(NotImplementedError):
-        mb.get_loss(d["atom_type"], d["r_feat"], d["p_feat"], ref["pos"].to(DEV), d["bond_index"], d["bond_type"],
-                    d["batch"], None, g["num_graphs"])
     with torch.no_grad():
         loss = mb.get_loss(d["atom_type"], d["r_feat"], d["p_feat"], ref["pos"].to(DEV), d["bond_index"], d["bond_type"],
                            d["batch"], None, g["num_graphs"], time_step=ref["time_step"].to(DEV),
@@ -585,6 +583,8 @@ def test_get_loss_forward_vs_reference_golden(name, golden_loss, rxn0, syn4):
     assert drawn.shape == ref["loss"].shape and bool(torch.isfinite(drawn).all())
     ref = golden_loss["a_" + name]
     ma = make_model("dualenc", 0, DEV)
+    with pytest.raises(NotImplementedError):
+        ma.get_loss(d["atom_type"], ref["pos"].to(DEV), d["bond_index"], d["bond_type"], d["batch"], None, g["num_graphs"])
     with torch.no_grad():
         loss, lg, ll = ma.get_loss(d["atom_type"], ref["pos"].to(DEV), d["bond_index"], d["bond_type"], d["batch"], None,
                                    g["num_graphs"], return_unreduced_loss=True, time_step=ref["time_step"].to(DEV),
