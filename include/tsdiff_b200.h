@@ -263,6 +263,19 @@ int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float
                  const float* edge_attr, const tsd_pair_mlp_t* mlp, int32_t accumulate, float* ef0,
                  float* edge_inv, int32_t math, tsd_stream_t stream);
 
+/* The second graph of path B costs a fraction of the first: its edge embedding differs only on the rows whose packed
+ * type codes differ (condensenc.py:219-234; the 4-hop pairs for edge_order 4 / pred_edge_order 3).
+ * tsd_edge_embed_delta compacts those rows (diff_rows ascending, diff_pos[m] = position or -1, *diff_count on the
+ * device), runs edge_cat on them only (d_emb from the first call, codes code1) into out_compact; tsd_pair_mlp_delta
+ * is tsd_pair_mlp whose edge_attr of row m is alt_attr[alt_pos[m]] where alt_pos[m] >= 0.  Bit-identical per row to
+ * the full evaluation.  All index arrays have edge_capacity entries. */
+int tsd_edge_embed_delta(const tsd_batch_t* batch, const tsd_edges_t* edges, const int32_t* code0, const int32_t* code1,
+                         const tsd_edge_encoder_t* enc, const float* d_emb, float* tmp, float* out_compact,
+                         int32_t* diff_rows, int32_t* diff_pos, int32_t* diff_count, int32_t math, tsd_stream_t stream);
+int tsd_pair_mlp_delta(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* h, const float* edge_attr,
+                       const float* alt_attr, const int32_t* alt_pos, const tsd_pair_mlp_t* mlp, int32_t accumulate,
+                       float* ef0, float* edge_inv, int32_t math, tsd_stream_t stream);
+
 /* ---- K7: eq_transform + clip + position update + centring + NaN flag, one launch
  * (replaces models/geometry.py:22-30, models/sampler.py:208-254 -- the `ld` branch :238-244 and the
  * `ddpm` branch :215-236 --, :260-268 and models/epsnet/dualenc.py:827-849,946-965).

@@ -105,6 +105,10 @@ _SIGNATURES = {
     "tsd_gine_layer": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Gine), _P, _P, _P, _P, C.c_int32, _P],
     "tsd_pair_mlp": [C.POINTER(Batch), C.POINTER(Edges), _P, _P, C.POINTER(PairMlp), C.c_int32, _P, _P, C.c_int32,
                      _P],
+    "tsd_edge_embed_delta": [C.POINTER(Batch), C.POINTER(Edges), _P, _P, C.POINTER(EdgeEncoder), _P, _P, _P, _P, _P, _P,
+                             C.c_int32, _P],
+    "tsd_pair_mlp_delta": [C.POINTER(Batch), C.POINTER(Edges), _P, _P, _P, _P, C.POINTER(PairMlp), C.c_int32, _P, _P,
+                           C.c_int32, _P],
     "tsd_ld_step": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.POINTER(ScoreChannel),
                     C.POINTER(LdParams), _P],
     "tsd_eq_transform": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(ScoreChannel), C.c_float, _P, _P],

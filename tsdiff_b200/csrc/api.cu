@@ -164,6 +164,82 @@ extern "C" int tsd_edge_embed(const tsd_batch_t* batch, const tsd_edges_t* edges
   return TSD_OK;
 }
 
+// Rows whose two packed type codes differ, in ascending order: diff_rows[0 .. *diff_count), and for every row its
+// position in that list or -1.  One CTA walks the rows in chunks of 1024 (ballot ranks + a 32-entry scan per chunk).
+__global__ void __launch_bounds__(1024) k_code_delta(const int* __restrict__ rows_dev, int rows_cap,
+                                                     const int* __restrict__ code0, const int* __restrict__ code1,
+                                                     int* __restrict__ diff_rows, int* __restrict__ diff_pos,
+                                                     int* __restrict__ diff_count) {
+  __shared__ int warp_off[32];
+  __shared__ int chunk_total;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = min(*rows_dev, rows_cap);
+  int base = 0;
+  for (int m0 = 0; m0 < M; m0 += 1024) {
+    const int m = m0 + tid;
+    const bool d = m < M && code0[m] != code1[m];
+    const unsigned bal = __ballot_sync(TSD_FULL_MASK, d);
+    if (lane == 0) warp_off[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      const int c = warp_off[lane];
+      int inc = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(TSD_FULL_MASK, inc, o);
+        if (lane >= o) inc += t;
+      }
+      warp_off[lane] = inc - c;
+      if (lane == 31) chunk_total = inc;
+    }
+    __syncthreads();
+    if (m < M) {
+      const int pos = base + warp_off[warp] + __popc(bal & tsd_lanemask_lt());
+      diff_pos[m] = d ? pos : -1;
+      if (d) diff_rows[pos] = m;
+    }
+    base += chunk_total;
+    __syncthreads();
+  }
+  if (tid == 0) *diff_count = base;
+}
+
+// Second graph of path B (condensenc.py:219-234): its edge embedding differs from the first graph's only on the rows
+// whose type codes differ (the 4-hop pairs when edge_order = 4 and pred_edge_order = 3: a fifth of the pairs), so
+// edge_cat runs on the compact list of those rows and consumers read `out_compact[diff_pos[m]]` where diff_pos[m] >= 0
+// and the first graph's edge_attr elsewhere (tsd_pair_mlp_delta).  Same arithmetic per row as tsd_edge_embed.
+extern "C" int tsd_edge_embed_delta(const tsd_batch_t* batch, const tsd_edges_t* edges, const int32_t* code0,
+                                    const int32_t* code1, const tsd_edge_encoder_t* enc, const float* d_emb, float* tmp,
+                                    float* out_compact, int32_t* diff_rows, int32_t* diff_pos, int32_t* diff_count,
+                                    int32_t math, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && code0 && code1 && enc && enc->cat0 && enc->cat2 && enc->bond_emb && d_emb && tmp &&
+              out_compact && diff_rows && diff_pos && diff_count);
+  const int H = enc->lin1.out_features;
+  TSD_REQUIRE(enc->cat0->in_features == 2 * H && enc->cat0->out_features == H);
+  cudaStream_t s = tsd_cu(stream);
+  if (batch->edge_capacity == 0) return TSD_OK;
+  k_code_delta<<<1, 1024, 0, s>>>(edges->num_edges, batch->edge_capacity, code0, code1, diff_rows, diff_pos, diff_count);
+  TSD_LAUNCH_CHECK();
+  GemmArgs g = edge_gemm(batch, edges, *enc->cat0);
+  g.M_ptr = diff_count;
+  g.a_kind = TSD_A_CAT;
+  g.A = d_emb;
+  g.lda = H;
+  g.H = H;
+  g.emb = enc->bond_emb;
+  g.code = code1;
+  g.row_index = diff_rows;
+  g.act = enc->cat_act;
+  g.C = tmp;
+  g.round_out = 1;
+  TSD_TRY(tsd_gemm(g, math, s));
+  GemmArgs g2 = edge_gemm(batch, edges, *enc->cat2);
+  g2.M_ptr = diff_count;
+  g2.A = tmp;
+  g2.C = out_compact;
+  g2.round_out = 1;
+  return tsd_gemm(g2, math, s);
+}
+
 extern "C" int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                                 const tsd_interaction_t* blk, const float* h_in, float* h_out, float* ef0, float* ef1,
                                 float* nf0, float* nf1, float* nf2, int32_t math, tsd_stream_t stream) {
@@ -232,7 +308,14 @@ extern "C" int tsd_gine_layer(const tsd_batch_t* batch, const tsd_edges_t* edges
 extern "C" int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* h, const float* edge_attr,
                             const tsd_pair_mlp_t* mlp, int32_t accumulate, float* ef0, float* edge_inv, int32_t math,
                             tsd_stream_t stream) {
-  TSD_REQUIRE(batch && edges && h && edge_attr && mlp && ef0 && edge_inv);
+  return tsd_pair_mlp_delta(batch, edges, h, edge_attr, nullptr, nullptr, mlp, accumulate, ef0, edge_inv, math, stream);
+}
+
+extern "C" int tsd_pair_mlp_delta(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* h,
+                                  const float* edge_attr, const float* alt_attr, const int32_t* alt_pos,
+                                  const tsd_pair_mlp_t* mlp, int32_t accumulate, float* ef0, float* edge_inv, int32_t math,
+                                  tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && h && edge_attr && mlp && ef0 && edge_inv && ((alt_attr == nullptr) == (alt_pos == nullptr)));
   TSD_REQUIRE(mlp->l2.out_features == 1 && mlp->l2.in_features == mlp->l1.out_features);
   cudaStream_t s = tsd_cu(stream);
   const int H = mlp->l0.in_features / 2;
@@ -244,6 +327,8 @@ extern "C" int tsd_pair_mlp(const tsd_batch_t* batch, const tsd_edges_t* edges, 
   g.h = h;
   g.row = edges->row;
   g.col = edges->col;
+  g.alt_A = alt_attr;
+  g.alt_pos = alt_pos;
   g.act = mlp->act;
   g.C = ef0;
   g.round_out = 1;  // feeds l1

@@ -32,6 +32,9 @@ struct GemmArgs {
   int act0;
   const float* emb;  // A_CAT: (100, H) bond embedding; code = row_lo | row_hi << 16
   const int* code;
+  const int* row_index;  // A_CAT, optional: logical row m reads d_emb / code of row row_index[m] (compact row lists)
+  const float* alt_A;    // A_PAIR, optional: rows with alt_pos[m] >= 0 take their edge_attr from alt_A[alt_pos[m]]
+  const int* alt_pos;
   const float* h;    // A_PAIR
   const int* row;
   const int* col;
@@ -90,11 +93,12 @@ __device__ __forceinline__ float4 tsd_load_a4_t(const GemmArgs& p, int m, int k)
     return tsd_act4_rt(p.act0, make_float4(fmaf(l, w.x, b.x), fmaf(l, w.y, b.y), fmaf(l, w.z, b.z), fmaf(l, w.w, b.w)));
   }
   if (AKIND == TSD_A_CAT) {
-    const int code = p.code[m];
+    const int src = p.row_index ? p.row_index[m] : m;
+    const int code = p.code[src];
     const int hi = k >= p.H;
     const int kk = k - (hi ? p.H : 0);
     const int r = hi ? ((unsigned)code >> 16) : (code & 0xffff);
-    const float4 d = *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + kk);
+    const float4 d = *reinterpret_cast<const float4*>(p.A + (size_t)src * p.lda + kk);
     const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)r * p.H + kk));
     return make_float4(d.x * e.x, d.y * e.y, d.z * e.z, d.w * e.w);
   }
@@ -104,6 +108,8 @@ __device__ __forceinline__ float4 tsd_load_a4_t(const GemmArgs& p, int m, int k)
       const float4 b = *reinterpret_cast<const float4*>(p.h + (size_t)p.col[m] * p.H + k);
       return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
     }
+    const int alt = p.alt_pos ? p.alt_pos[m] : -1;
+    if (alt >= 0) return *reinterpret_cast<const float4*>(p.alt_A + (size_t)alt * p.lda + (k - p.H));
     return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + (k - p.H));
   }
   return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);

@@ -46,19 +46,24 @@ __host__ __device__ constexpr int tc_group_threads(int nt) { return (nt - 64) / 
 // (length / packed bond codes / row+col atom ids) is loaded ONCE before the K loop: the panel
 // loads then have no dependent index load in front of them.
 template <int AKIND>
-__device__ __forceinline__ void tc_row_meta(const GemmArgs& p, int m, int& meta0, int& meta1) {
+__device__ __forceinline__ void tc_row_meta(const GemmArgs& p, int m, int& meta0, int& meta1, int& meta2) {
   meta0 = 0;
   meta1 = 0;
+  meta2 = -1;
   if (AKIND == TSD_A_EDGE_MLP0) meta0 = __float_as_int(p.len[m]);
-  if (AKIND == TSD_A_CAT) meta0 = p.code[m];
+  if (AKIND == TSD_A_CAT) {
+    meta1 = p.row_index ? p.row_index[m] : m;  // source row of d_emb / code (compact row lists)
+    meta0 = p.code[meta1];
+  }
   if (AKIND == TSD_A_PAIR) {
     meta0 = p.row[m];
     meta1 = p.col[m];
+    if (p.alt_pos) meta2 = p.alt_pos[m];       // >= 0: the row's edge_attr lives in alt_A
   }
 }
 
 template <int AKIND>
-__device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, int meta0, int meta1) {
+__device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, int meta0, int meta1, int meta2) {
   if (AKIND == TSD_A_EDGE_MLP0) {
     const float l = __int_as_float(meta0);
     const float4 w = __ldg(reinterpret_cast<const float4*>(p.w0 + k));
@@ -81,7 +86,7 @@ __device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, in
     const int hi = k >= p.H;
     const int kk = k - (hi ? p.H : 0);
     const int r = hi ? ((unsigned)meta0 >> 16) : (meta0 & 0xffff);
-    const float4 d = *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + kk);
+    const float4 d = *reinterpret_cast<const float4*>(p.A + (size_t)meta1 * p.lda + kk);
     const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + (size_t)r * p.H + kk));
     return make_float4(d.x * e.x, d.y * e.y, d.z * e.z, d.w * e.w);
   }
@@ -91,7 +96,8 @@ __device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, in
       const float4 b = *reinterpret_cast<const float4*>(p.h + (size_t)meta1 * p.H + k);
       return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
     }
-    return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + (k - p.H));
+    const float* src = meta2 >= 0 ? p.alt_A + (size_t)meta2 * p.lda : p.A + (size_t)m * p.lda;
+    return *reinterpret_cast<const float4*>(src + (k - p.H));
   }
   return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);
 }
@@ -186,10 +192,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
     constexpr int ROW_STEP = TC_GROUP_THREADS / 8;                              // rows between a thread's items
     constexpr int ITEMS = (TC_BM * 8 + TC_GROUP_THREADS - 1) / TC_GROUP_THREADS;  // float4 per thread per panel
     const int chunk = t & 7, row0 = t >> 3;  // item i -> row row0 + ROW_STEP i, 16-byte chunk `chunk`
-    int meta0[ITEMS], meta1[ITEMS];
+    int meta0[ITEMS], meta1[ITEMS], meta2[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)  // rows past M are clamped: they only feed output rows that are never stored
-      tc_row_meta<AKIND>(p, min(m0 + min(row0 + ROW_STEP * i, TC_BM - 1), M - 1), meta0[i], meta1[i]);
+      tc_row_meta<AKIND>(p, min(m0 + min(row0 + ROW_STEP * i, TC_BM - 1), M - 1), meta0[i], meta1[i], meta2[i]);
     for (int kb = group; kb < num_kb; kb += TC_GROUPS) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i)  // branch-free on purpose: a per-item `m < M` branch serialises the loads
         v[i] = tf32_rn4(
-            tc_load_a4<AKIND>(p, min(m0 + min(row0 + ROW_STEP * i, TC_BM - 1), M - 1), k, meta0[i], meta1[i]));
+            tc_load_a4<AKIND>(p, min(m0 + min(row0 + ROW_STEP * i, TC_BM - 1), M - 1), k, meta0[i], meta1[i], meta2[i]));
 #pragma unroll
       for (int i = 0; i < ITEMS; ++i)
         if ((TC_BM * 8) % TC_GROUP_THREADS == 0 || i < ITEMS - 1 || row0 + ROW_STEP * i < TC_BM)

@@ -342,6 +342,11 @@ class CondensedScoreEngine:
         self.nf_pool, self.nf_pool_count = _node_pool(plan, h, math)
         self.ef_pool, self.ef_pool_count = _filter_pool(plan, h, len(models[0].encoder.interactions), math)
         self.edge_inv = torch.zeros(max(plan.work_capacity, 1), dtype=torch.float32, device=plan.device)
+        # second graph: rows whose type codes differ from the first graph's (tsd_edge_embed_delta)
+        cap = max(plan.work_capacity, 1)
+        self.diff_rows = torch.zeros(cap, dtype=torch.int32, device=plan.device)
+        self.diff_pos = torch.full((cap,), -1, dtype=torch.int32, device=plan.device)
+        self.diff_count = torch.zeros(1, dtype=torch.int32, device=plan.device)
         atom_type = atom_type.to(torch.long).contiguous()
         r_feat = _integer_features(r_feat, "r_feat")
         p_feat = _integer_features(p_feat, "p_feat")
@@ -388,15 +393,16 @@ class CondensedScoreEngine:
                 # idle.  It is ENQUEUED after the encoder so the first filter kernel is not queued behind it.
                 self.side.wait_event(fork)
                 with torch.cuda.stream(self.side):
-                    L.check(lib.tsd_edge_embed(b, e, L.ptr(plan.work_tab1), enc, 1, L.ptr(d_emb), L.ptr(tmp2), L.ptr(ea2),
-                                               self.math, _stream()), "tsd_edge_embed")
-                ea_out = ea2
-            else:
-                ea_out = ea1
-            if self.two_graphs:
+                    L.check(lib.tsd_edge_embed_delta(b, e, L.ptr(plan.work_tab0), L.ptr(plan.work_tab1), enc, L.ptr(d_emb),
+                                                     L.ptr(tmp2), L.ptr(ea2), L.ptr(self.diff_rows), L.ptr(self.diff_pos),
+                                                     L.ptr(self.diff_count), self.math, _stream()), "tsd_edge_embed_delta")
                 main.wait_stream(self.side)
-            L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_out), C.byref(mem["pair"]), 1 if mi > 0 else 0,
-                                     L.ptr(ef0), L.ptr(self.edge_inv), self.math, s), "tsd_pair_mlp")
+                L.check(lib.tsd_pair_mlp_delta(b, e, L.ptr(hbuf), L.ptr(ea1), L.ptr(ea2), L.ptr(self.diff_pos),
+                                               C.byref(mem["pair"]), 1 if mi > 0 else 0, L.ptr(ef0), L.ptr(self.edge_inv),
+                                               self.math, s), "tsd_pair_mlp_delta")
+            else:
+                L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea1), C.byref(mem["pair"]), 1 if mi > 0 else 0,
+                                         L.ptr(ef0), L.ptr(self.edge_inv), self.math, s), "tsd_pair_mlp")
 
     def score_channels(self, clip):
         ch0 = L.ScoreChannel(self.edge_inv.data_ptr(), self.plan.in_b.data_ptr(), 1 if self.two_graphs else 0,
