@@ -6,12 +6,8 @@ import ctypes as C, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "profiles", "ubench", "variants")
-VARIANTS = {
-    "r1node": dict(TSD_EXP_OLD_NODE=1, TSD_EXP_SPLIT_ACC=0),
-    "new": dict(TSD_EXP_SPLIT_ACC=0),
-    "new_nopool": dict(TSD_EXP_SPLIT_ACC=0, TSD_EXP_FILTER_POOL=0),
-}
-TILES = {"r1node": (0,), "new": (161, 321, 481, 641, 322, 644), "new_nopool": (161, 481)}
+VARIANTS = {"new": dict()}
+TILES = {"new": (321, 481, 641)}
 
 
 def build():

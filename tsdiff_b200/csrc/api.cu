@@ -507,7 +507,8 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     // aggregation fused in front of the three linears as transposed (swap-AB) tensor-core GEMMs
     // (node_update.cu).  x1 ping-pongs between nf0 and nf1: a CTA's aggregation gathers x1 rows of atoms
     // that other CTAs own, so the next block's x1 must not overwrite them.
-    const int tile = tsd_node_tile(batch->num_nodes);
+    int npc = 0;
+    const int tile = tsd_node_tile(batch->num_nodes, tsd_ceil_div(batch->edge_capacity, 128), &npc);
     float* x1buf[2] = {nf0, nf1};
     // filter buffers: ef1, ef0, then the optional pool (one per block lets every filter kernel run ahead)
     float* fbuf[EncoderFork::MAX_BLOCKS];
@@ -522,6 +523,7 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     NodeArgs na;
     memset(&na, 0, sizeof(na));
     na.num_nodes = batch->num_nodes;
+    na.nodes_per_cluster = npc;
     na.H = H;
     na.x = h_in;  // x1 of block 0
     na.num_stages = 1;
@@ -550,6 +552,7 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
       TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
       memset(&na, 0, sizeof(na));
       na.num_nodes = batch->num_nodes;
+      na.nodes_per_cluster = npc;
       na.H = H;
       na.in_ptr = edges->in_ptr;
       na.in_eid = edges->in_eid;

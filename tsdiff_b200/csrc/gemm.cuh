@@ -157,6 +157,7 @@ struct NodeStage {
 
 struct NodeArgs {
   int num_nodes, H, num_stages;
+  int nodes_per_cluster;  // atoms a cluster owns (<= the kernel's NT: the MMA shape is padded); 0 = NT
   const float* x;  // dense (N, H) input of stage 0, or NULL -> fused CFConv aggregation of the fields below
   const int* in_ptr;
   const int* in_eid;
@@ -166,7 +167,7 @@ struct NodeArgs {
   NodeStage st[3];
 };
 
-int tsd_node_tile(int num_nodes);                                       // node_update.cu: atoms per CTA
+int tsd_node_tile(int num_nodes, int filter_tiles, int* nodes_per_cluster);  // node_update.cu: kernel shape
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream);
 int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream);           // gemm_chain.cu
 int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream);        // dispatch (api.cu)

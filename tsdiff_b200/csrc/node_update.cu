@@ -198,8 +198,11 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
   if (tid == 0) NU_STAMP(0);
   const uint32_t rank = C > 1 ? nu_cluster_rank() : 0u;
   const bool leader = rank == 0;
-  const int node0 = (blockIdx.x / C) * NT;  // first atom of the cluster's tile
-  const int N = p.num_nodes;
+  // a cluster owns `npc` <= NT atoms (the MMA shape N = NT is padded): the host picks npc so that the node CTAs fit on the
+  // SMs the concurrently running filter kernel leaves free, which matters more than an exactly filled tile
+  const int npc = p.nodes_per_cluster > 0 ? min(p.nodes_per_cluster, NT) : NT;
+  const int node0 = (blockIdx.x / C) * npc;  // first atom of the cluster's tile
+  const int N = min(p.num_nodes, node0 + npc);  // atoms past the tile belong to the next cluster
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
   uint8_t* xbuf = smem_gen;                       // B operand (leader); rewritten in place by every epilogue
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
       for (int item = warp; item < ITEMS; item += NU_WORKERS) {
         const int n = item / SL, slab = item - n * SL;
         const int off = slab * 128 + lane * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the tile: zeros (their output columns are never stored)
         if (node0 + my0 + n < N) acc = nu_aggregate_item(p, eids, srcs, s_ptr[n], s_ptr[n + 1], off, lane);
         nu_st_cluster4(xdst + (uint32_t)((off >> 5) * X_PANEL) + sw128_off(my0 + n, (off & 31) >> 2), tf32_rn4(acc));
       }
@@ -355,6 +358,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
 #pragma unroll 1
         for (int cc = 0; cc < CW; cc += CWC) {
           const int n0 = cs * CW + cc;
+          if (waited && node0 + n0 >= N) break;  // columns of atoms past the tile (padding of the MMA shape)
           float res[CWC];
           if (epi_warp && st_res) {  // independent of the accumulator: in flight behind the MMA
 #pragma unroll
@@ -415,10 +419,11 @@ int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
     TSD_CUDA(cudaFuncSetAttribute(k_node_update<H, NT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  int tmem_cols = 2 * (H / 128) * NT;
-  if (tmem_cols < 32) tmem_cols = 32;
+  int tmem_cols = 32;  // a power of two >= 32 that holds 2 accumulator sets x H/128 halves x NT columns
+  while (tmem_cols < 2 * (H / 128) * NT) tmem_cols *= 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tsd_ceil_div(a.num_nodes, NT) * C);
+  const int npc = a.nodes_per_cluster > 0 && a.nodes_per_cluster < NT ? a.nodes_per_cluster : NT;
+  cfg.gridDim = dim3(tsd_ceil_div(a.num_nodes, npc) * C);
   cfg.blockDim = dim3(NU_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -446,11 +451,19 @@ static int g_node_tile_override = 0;
 // 0 restores the built-in choice
 extern "C" void tsd_tune_node_tile(int code) { g_node_tile_override = code; }
 
-// atoms per cluster * 10 + CTAs per cluster
-int tsd_node_tile(int num_nodes) {
-  if (g_node_tile_override > 0) return g_node_tile_override;
+// Kernel shape (atoms per cluster * 10 + CTAs per cluster) and the atoms a cluster really takes (0 = all of the shape).
+// 32 atoms per single CTA measured best at batch 100 (profiles/r2_variants_*.txt): fewer atoms per CTA shorten the
+// aggregation phase (bound by one SM's L2 ingest, 127 GB/s) but multiply the weight streams and the CTAs that compete
+// with the concurrently running filter kernels for SMs; more atoms per CTA (48, 64) or cluster variants that hand the
+// rows to a leader CTA lengthen the serial node chain.  Sizing the tile so that node + filter CTAs exactly fit the 148
+// SMs (tried: atoms per CTA derived from the edge capacity) only pays when the edge count is far below its capacity,
+// which a trained model's late trajectory is not (every pair inside the cutoff: 132 filter tiles at batch 100).
+int tsd_node_tile(int num_nodes, int filter_tiles, int* nodes_per_cluster) {
   (void)num_nodes;
-  return 321;  // 32 atoms per CTA: at batch 100 the 55 node CTAs fit beside the 94 filter tiles (profiles/r2_variants.txt)
+  (void)filter_tiles;
+  *nodes_per_cluster = 0;
+  if (g_node_tile_override > 0) return g_node_tile_override;
+  return 321;
 }
 
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
@@ -470,6 +483,7 @@ int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
     return a.H == 256 ? node_launch<256, NT, C>(a, maps, stream) : node_launch<128, NT, C>(a, maps, stream)
   NU_GO(16, 1);
   NU_GO(32, 1);
+  NU_GO(48, 1);
   NU_GO(64, 1);
   NU_GO(32, 2);
   NU_GO(64, 4);
