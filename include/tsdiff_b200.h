@@ -222,6 +222,16 @@ int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const
                        int32_t nf_pool_count, float* ef_pool, int32_t ef_pool_count, int32_t math,
                        tsd_stream_t stream);
 
+/* The node side of one InteractionBlock as ONE tensor-core kernel (tf32; what tsd_schnet_encoder launches per block when
+ * the batch has few atoms -- schnet.py:101-104,124-128 and the next block's :101):
+ *   agg_i = sum_{j->i} x1_j * filt_ji;  h_out = h_in + lin(ssp(lin2(agg)));  x1_next = next_lin1(h_out)
+ * The segmented aggregation (in-CSR, ascending source order, no atomics) is the B-operand producer of transposed
+ * ("swap AB") tcgen05 GEMMs: M = 128 output features, N = 32 atoms per CTA, weights streamed by TMA.
+ * next_lin1 / x1_next may both be NULL (last block).  x1_next must not alias x1; h_out may alias h_in. */
+int tsd_interaction_node_update(const tsd_batch_t* batch, const tsd_edges_t* edges, const tsd_interaction_t* blk,
+                                const tsd_linear_t* next_lin1, const float* x1, const float* filt, const float* h_in,
+                                float* h_out, float* x1_next, tsd_stream_t stream);
+
 /* The two building blocks of K4, exposed on their own for unit tests and for the per-kernel
  * roofline timing in bench.py:
  *  tsd_linear          : out = act(x W^T + b) for a dense (rows, in) x; `rows_dev` (device int,

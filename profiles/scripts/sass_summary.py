@@ -2,7 +2,7 @@
 (cuobjdump -sass; no GPU needed).   python profiles/scripts/sass_summary.py > profiles/r2_sass_summary.txt
   UTCHMMA  tcgen05.mma       LDTM  tcgen05.ld (TMEM -> registers)    UTMALDG  cp.async.bulk.tensor (TMA load)
   UTCBAR   tcgen05.commit    SYNCS mbarrier ops                      UCGABAR  cluster barrier
-  MUFU     SFU ops (ex2 / lg2 / rcp)   FFMA  fp32 FMA   ST.E/STS ... with .cluster suffixes: distributed shared memory"""
+  MUFU     SFU ops (ex2 / lg2 / rcp)   FFMA  fp32 FMA   HMMA  legacy mma.sync path (expected: 0)"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 lib = os.path.join(ROOT, "tsdiff_b200", "libtsdiff_b200.so")
@@ -20,7 +20,7 @@ for line in out.splitlines():
     if cur and re.search(r"/\*[0-9a-f]{4,}\*/", line):
         sizes[cur] += 1
         for k in KEYS:
-            if k in line:
+            if (re.search(r"(?<![A-Z])HMMA", line) if k == "HMMA" else k in line):
                 counts[cur][k] += 1
 demangle = subprocess.run(["cu++filt"] + list(counts), capture_output=True, text=True).stdout.splitlines()
 print("# %s  (sm_100a, %d kernels)" % (os.path.relpath(lib, ROOT), len(counts)))

@@ -190,3 +190,51 @@ def test_stress_shape_tf32_asymmetric_pairs_and_ld():
                                     step_lr=1e-7, clip=1000, sampling_type="ld", noise=noise)
         traj[math] = torch.stack(t)
     assert (traj["tf32"] - traj["fp32"]).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize("h,last", [(256, False), (256, True), (128, False)])
+def test_interaction_node_update_kernel_vs_fp64(h, last, syn4):
+    """k_node_update alone (the fused CFConv aggregation + transposed tcgen05 node linears) against an fp64 torch
+    evaluation of the same operator on a replicated golden graph (N = 1024 atoms, ragged last tile): h_out and x1_next
+    within the single-GEMM tf32 bound (1.5e-3 L2-relative); the aggregation inside is exact in fp32 before rounding."""
+    from tsdiff_b200 import engine as E
+    reps = 16
+    n1 = syn4["atom_type"].numel()
+    d = to_dev(syn4, DEV)
+    batch = torch.cat([d["batch"] + i * syn4["num_graphs"] for i in range(reps)])
+    bond_index = torch.cat([d["bond_index"] + i * n1 for i in range(reps)], dim=1)
+    plan = E.BatchPlan(0, batch, bond_index, d["bond_type"].repeat(reps), 4, 3, upairs=True)
+    pos = (syn4["pos_init"] * 3.0).repeat(reps, 1).to(DEV).contiguous()
+    plan.build_edges(pos, 10.0)
+    n, e, u = plan.num_nodes, plan.edge_count(), plan.work_count()
+    torch.manual_seed(h + last)
+    lib = L.load()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def rounded(t):
+        out = torch.empty_like(t)
+        L.check(lib.tsd_round_tf32(L.ptr(t), L.ptr(out), t.numel(), s), "round")
+        return out
+    w2, wl, w1 = (rounded(torch.randn(h, h, device=DEV) / h ** 0.5) for _ in range(3))
+    b2, bl = torch.randn(h, device=DEV), torch.randn(h, device=DEV)
+    x1 = torch.randn(n, h, device=DEV)
+    filt = torch.randn(max(plan.work_capacity, 1), h, device=DEV)
+    h_in = torch.randn(n, h, device=DEV)
+    h_out, x1_next = torch.full((n, h), 7.0, device=DEV), torch.full((n, h), 7.0, device=DEV)
+    blk = L.Interaction()
+    blk.lin2, blk.lin = L.linear(w2, b2), L.linear(wl, bl)
+    nxt = L.linear(w1, None)
+    L.check(lib.tsd_interaction_node_update(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), C.byref(blk),
+                                            None if last else C.byref(nxt), L.ptr(x1), L.ptr(filt), L.ptr(h_in), L.ptr(h_out),
+                                            None if last else L.ptr(x1_next), s), "tsd_interaction_node_update")
+    torch.cuda.synchronize()
+    row, col = plan.row[:e].long(), plan.col[:e].long()
+    pair = plan.edge_upair[:e].long()
+    agg = torch.zeros(n, h, dtype=torch.float64, device=DEV).index_add_(0, col, x1.double()[row] * filt.double()[pair])
+    y = torch.nn.functional.softplus(agg @ w2.double().t() + b2.double()) - 0.6931471805599453
+    ref_h = h_in.double() + y @ wl.double().t() + bl.double()
+    assert 1e-6 < rel_err(h_out, ref_h) < 1.5e-3
+    if not last:
+        assert 1e-6 < rel_err(x1_next, ref_h @ w1.double().t()) < 2.5e-3  # three chained tf32 GEMMs
+    else:
+        assert bool((x1_next == 7.0).all())

@@ -374,6 +374,44 @@ extern "C" int tsd_cfconv_aggregate(const tsd_batch_t* batch, const tsd_edges_t*
   return tsd_aggregate(batch, edges, channels, x1, filt, agg, tsd_cu(stream));
 }
 
+// The node side of one interaction block as ONE kernel (node_update.cu): aggregation fused in front of the linears.
+extern "C" int tsd_interaction_node_update(const tsd_batch_t* batch, const tsd_edges_t* edges, const tsd_interaction_t* blk,
+                                           const tsd_linear_t* next_lin1, const float* x1, const float* filt,
+                                           const float* h_in, float* h_out, float* x1_next, tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && blk && x1 && filt && h_in && h_out && ((next_lin1 == nullptr) == (x1_next == nullptr)));
+  TSD_REQUIRE(x1_next != x1);  // other CTAs still gather x1 rows while this one writes
+  const int H = blk->lin.out_features;
+  TSD_REQUIRE(blk->lin2.in_features == H && blk->lin2.out_features == H && blk->lin.in_features == H);
+  NodeArgs na;
+  memset(&na, 0, sizeof(na));
+  int npc = 0;
+  const int tile = tsd_node_tile(batch->num_nodes, tsd_ceil_div(batch->edge_capacity, 128), &npc);
+  na.num_nodes = batch->num_nodes;
+  na.nodes_per_cluster = npc;
+  na.H = H;
+  na.in_ptr = edges->in_ptr;
+  na.in_eid = edges->in_eid;
+  na.in_src = edges->in_src;
+  na.x1 = x1;
+  na.filt = filt;
+  na.st[0].W = blk->lin2.weight;
+  na.st[0].bias = blk->lin2.bias;
+  na.st[0].act = TSD_ACT_SSP;
+  na.st[1].W = blk->lin.weight;
+  na.st[1].bias = blk->lin.bias;
+  na.st[1].residual = h_in;
+  na.st[1].store = h_out;
+  na.num_stages = 2;
+  if (next_lin1) {
+    TSD_REQUIRE(next_lin1->in_features == H && next_lin1->out_features == H);
+    na.st[2].W = next_lin1->weight;
+    na.st[2].bias = next_lin1->bias;
+    na.st[2].store = x1_next;
+    na.num_stages = 3;
+  }
+  return tsd_node_update_tf32(na, tile, tsd_cu(stream));
+}
+
 // library-owned side stream + events for the fork/join inside tsd_schnet_encoder
 struct EncoderFork {
   static const int MAX_BLOCKS = 32;
