@@ -369,7 +369,22 @@ def kernel_rooflines(args, eng, peaks, device):
            "peak_source": peaks["source"], "us_per_launch": t_agg * 1e6, "algorithmic_bytes": nbytes,
            "regime": "batch 100: 34 MB per launch, L2 resident inside the step -- latency bound, not HBM bound; the "
                      "HBM-bound regime is roofline_stress"}
-    return tensor, hbm
+    node = None
+    if tf32 and hasattr(lib, "tsd_interaction_node_update"):
+        # the fused node kernel of one interaction block (aggregation + lin2 -> ssp -> lin -> +h -> next lin1)
+        nxt = L.linear(ws.node[0].new_zeros(h, h), None)
+        hb, x1n, hout = ws.node[0], ws.node[3], ws.node[2]
+        t_n = timed_cold(lambda: L.check(lib.tsd_interaction_node_update(
+            C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), C.byref(blocks[0]), C.byref(nxt), L.ptr(x1), L.ptr(out),
+            L.ptr(hb), L.ptr(hout), L.ptr(x1n), stream), "tsd_interaction_node_update"), flush)
+        nb = nbytes + 3 * n * h * 4 + 3 * h * h * 4  # + h in, h out, x1_next, three weight matrices
+        node = {"bound": "hbm", "kernel": "k_node_update: CFConv aggregation fused into the node linears (swap-AB tcgen05, "
+                                          "32 atoms per CTA)", "achieved": nb / t_n / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": nb / t_n / 1e9 / peaks["hbm"], "traffic": traffic.get("k_node_update"), "us_per_launch": t_n * 1e6,
+                "algorithmic_bytes": nb, "executed_flops": 3 * 2.0 * n * h * h,
+                "regime": "latency / per-SM ingest bound: every CTA gathers its atoms' filter rows through one SM's L2 port "
+                          "(127 GB/s measured, profiles/r2_tma_stream.txt) and streams the three weight matrices"}
+    return tensor, hbm, node
 
 
 def stress_rooflines(args, peaks, device):
@@ -643,7 +658,7 @@ def run_ours(args):
         runner.run(n_steps=min(args.ld_steps, 2000))  # a late-trajectory edge list (every pair inside the cutoff)
     mean_edges = eng.plan.edge_count()
     work_rows = eng.plan.work_count()
-    tensor_roof, hbm_roof = kernel_rooflines(args, eng, peaks, device)
+    tensor_roof, hbm_roof, node_roof = kernel_rooflines(args, eng, peaks, device)
     extras = {}
     plain = world == 1 and not ensemble_mode and args.members == 1 and not args.no_extras
     if plain and args.network == "condensenc" and args.math == "tf32":
@@ -659,7 +674,7 @@ def run_ours(args):
         rmsd = (torch.zeros(data["num_graphs"]).index_add_(0, data["batch"], diff2) / data["num_nodes_per_graph"]).sqrt()
         run32._reset()
         run32.run(n_steps=min(args.ld_steps, 2000))
-        roof32, _ = kernel_rooflines(a32, eng32, peaks, device)
+        roof32, _, _ = kernel_rooflines(a32, eng32, peaks, device)
         extras["strict_fp32"] = {"value": args.batch / t32, "unit": UNIT, "us_per_eps_step": t32 * 1e6 / args.ld_steps,
                                  "trajectories": 1, "ld_steps": args.ld_steps, "dtype": "f32",
                                  "bound": "eps <= 1e-4 relative per step (tests/test_gpu_kernels.py)", "roofline": roof32}
@@ -698,7 +713,8 @@ def run_ours(args):
            "us_per_sampler_step": ms_per_step * 1e3 / args.ld_steps,
            "gpu_launches": int(launches_per_ld_step) * args.ld_steps * args.steps,
            "launches_per_ld_step": int(launches_per_ld_step), "clocks": clock_info, "e2e": e2e,
-           "roofline": tensor_roof, "roofline_message_passing": hbm_roof, "cpu_baseline": cpu,
+           "roofline": tensor_roof, "roofline_message_passing": hbm_roof, "roofline_node_update": node_roof,
+           "cpu_baseline": cpu,
            "published_reference_datum": "<=39.5 ms/step, ~0.51 samples/s (DDPM, unnamed GPU; BASELINE.md)"}
     out.update(extras)
     if ens_extra is not None:
