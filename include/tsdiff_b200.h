@@ -203,6 +203,15 @@ int tsd_cfconv_layer(const tsd_batch_t* batch, const tsd_edges_t* edges, const f
 int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                        const tsd_interaction_t* blk, float* tmp, float* filt, int32_t math, tsd_stream_t stream);
 
+/* The filter networks of `num_blocks` consecutive interaction blocks in ONE tensor-core kernel (tf32 only;
+ * models/encoder/schnet.py:91-98 for every block of :203-225): filt[l] = nn2_l(ssp(nn0_l(edge_attr))) * C_l(len).
+ * The filters depend on edge_attr only, so a CTA keeps a 128-row tile and runs the 2 x num_blocks chained GEMMs with
+ * the TMA weight stream, the tcgen05 main loops and both epilogues overlapped (what tsd_schnet_encoder launches when it
+ * has one filter buffer per block).  `filt`: num_blocks device buffers (E_cap, H).  num_blocks <= 8, H in {128, 256},
+ * E_cap >= 1024; otherwise TSD_ERR_UNSUPPORTED (use tsd_filter_network per block). */
+int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                     const tsd_interaction_t* blocks, int32_t num_blocks, float* const* filt, tsd_stream_t stream);
+
 /* The whole SchNet encoder (models/encoder/schnet.py:203-225): `num_blocks` interaction blocks
  * applied in sequence, h_out = SchNet(h_in).  Same scratch as tsd_cfconv_layer.  In tf32 mode the
  * blocks run as chained tensor-core kernels (filter network fused on the edges; lin2 -> lin ->

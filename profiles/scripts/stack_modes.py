@@ -1,0 +1,37 @@
+"""Langevin-step time (CUDA-graph replays, late-trajectory edge count) for the filter-stack launch modes and node tiles
+in ONE process: the tuning hooks are run-time switches, every mode re-captures its graph.
+usage: python profiles/scripts/stack_modes.py [mode:tile:splitmma ...]   (mode -1 = one filter kernel per block)"""
+import sys, json, torch
+sys.path.insert(0, '.')
+import bench
+from tsdiff_b200 import _lib as L
+
+class A: pass
+args = A(); args.batch = 100; args.network = 'condensenc'; args.math = 'tf32'; args.ld_steps = 5000; args.members = 1; args.mode = 'shard'
+dev = torch.device('cuda:0')
+lib = L.load()
+data = bench.build_inputs(args, 0)
+model, cfg = bench.make_models(args, dev)
+dd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+specs = sys.argv[1:] or ["-1:0:0", "0:0:0"]
+ref_pos = None
+for spec in specs:
+    mode, tile, split = (int(x) for x in spec.split(":"))
+    lib.tsd_tune_filter_stack(mode)
+    lib.tsd_tune_node_tile(tile)
+    lib.tsd_tune_filter_stack_mma(split)
+    torch.manual_seed(0)
+    eng, runner = bench.build_runner(args, [model], dd, keep_traj=False)
+    runner.prepare(); runner.run(n_steps=1500); torch.cuda.synchronize()
+    pos = runner.pos.clone() if hasattr(runner, "pos") else None
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(1500): runner.graph.replay()
+    t1.record(); torch.cuda.synchronize()
+    out = {"mode": mode, "tile": tile, "split_mma": split, "step_us": t0.elapsed_time(t1) / 1500 * 1e3,
+           "pairs": eng.plan.work_count()}
+    if pos is not None:
+        if ref_pos is None: ref_pos = pos
+        out["max_abs_pos_diff_vs_first_mode"] = float((pos - ref_pos).abs().max())
+    print(json.dumps(out), flush=True)
+    del eng, runner

@@ -238,3 +238,61 @@ def test_interaction_node_update_kernel_vs_fp64(h, last, syn4):
         assert 1e-6 < rel_err(x1_next, ref_h @ w1.double().t()) < 2.5e-3  # three chained tf32 GEMMs
     else:
         assert bool((x1_next == 7.0).all())
+
+
+@pytest.mark.parametrize("h,layers,smooth", [(256, 7, False), (256, 3, True), (128, 6, False), (256, 1, False)])
+def test_filter_stack_kernel_vs_single_layer_kernels_and_fp64(h, layers, smooth, syn4):
+    """k_filter_stack (the filter networks of all interaction blocks in one launch, epilogues overlapped with the
+    tcgen05 main loops, TMA stores) on a replicated golden graph with a ragged last tile: (a) the same arithmetic as one
+    chained kernel per block (tsd_filter_network) -- equal to fp32 rounding of the epilogue, (b) against fp64 torch
+    within the two-GEMM tf32 bound, (c) rows past the pair count are not read by anyone: written as zeros."""
+    from tsdiff_b200 import engine as E
+    reps = 40
+    n1 = syn4["atom_type"].numel()
+    d = to_dev(syn4, DEV)
+    batch = torch.cat([d["batch"] + i * syn4["num_graphs"] for i in range(reps)])
+    bond_index = torch.cat([d["bond_index"] + i * n1 for i in range(reps)], dim=1)
+    plan = E.BatchPlan(0, batch, bond_index, d["bond_type"].repeat(reps), 4, 3, upairs=True)
+    pos = (syn4["pos_init"] * 3.0).repeat(reps, 1).to(DEV).contiguous()
+    plan.build_edges(pos, 10.0)
+    u, cap = plan.work_count(), plan.work_capacity
+    assert cap >= 1024 and u % 128 != 0
+    torch.manual_seed(h + layers)
+    lib = L.load()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def rounded(t):
+        out = torch.empty_like(t)
+        L.check(lib.tsd_round_tf32(L.ptr(t), L.ptr(out), t.numel(), s), "round")
+        return out
+    edge_attr = rounded(torch.randn(cap, h, device=DEV))
+    cutoff = 6.0  # some pairs of the scaled geometry lie outside
+    ws, blocks = [], []
+    for _ in range(layers):
+        w0, w2 = (rounded(torch.randn(h, h, device=DEV) / h ** 0.5) for _ in range(2))
+        b0, b2 = torch.randn(h, device=DEV), torch.randn(h, device=DEV)
+        blk = L.Interaction()
+        blk.nn0, blk.nn2 = L.linear(w0, b0), L.linear(w2, b2)
+        blk.cutoff, blk.smooth = cutoff, int(smooth)
+        ws.append((w0, b0, w2, b2))
+        blocks.append(blk)
+    arr = (L.Interaction * layers)(*blocks)
+    outs = [torch.full((cap, h), 7.0, device=DEV) for _ in range(layers)]
+    ptrs = (C.c_void_p * layers)(*[o.data_ptr() for o in outs])
+    L.check(lib.tsd_filter_stack(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), L.ptr(edge_attr), arr, layers,
+                                 ptrs, s), "tsd_filter_stack")
+    torch.cuda.synchronize()
+    length = (plan.u_length if plan.upairs else plan.length)[:u].double()
+    env = (0.5 * (torch.cos(length * torch.pi / cutoff) + 1.0) * (length <= cutoff)) if smooth else (length <= cutoff).double()
+    assert 0 < int((env == 0).sum()) < u
+    tmp, single = torch.empty(cap, h, device=DEV), torch.empty(cap, h, device=DEV)
+    for l, (w0, b0, w2, b2) in enumerate(ws):
+        L.check(lib.tsd_filter_network(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), L.ptr(edge_attr),
+                                       C.byref(blocks[l]), L.ptr(tmp), L.ptr(single), L.MATH["tf32"], s), "tsd_filter_network")
+        torch.cuda.synchronize()
+        assert (outs[l][:u] - single[:u]).abs().max() <= 1e-6 * single[:u].abs().max()
+        x = torch.nn.functional.softplus(edge_attr[:u].double() @ w0.double().t() + b0.double()) - 0.6931471805599453
+        ref = (x @ w2.double().t() + b2.double()) * env[:, None]
+        assert 1e-6 < rel_err(outs[l][:u], ref) < 1.5e-3
+        tail = outs[l][u:((u + 127) // 128) * 128]
+        assert bool((tail == 0).all()) and bool((outs[l][((u + 127) // 128) * 128:] == 7.0).all())

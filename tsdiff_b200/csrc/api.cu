@@ -491,6 +491,44 @@ extern "C" int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* e
   return tsd_gemm(g, math, s);
 }
 
+// The filter networks of blocks [0, num_blocks) in ONE kernel (filter_stack.cu; tf32 only): filt[l] = nn2_l(ssp(nn0_l(
+// edge_attr))) * C_l(len).  TSD_ERR_UNSUPPORTED when the shapes do not fit the kernel (callers fall back to one
+// tsd_filter_network per block).
+extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                                const tsd_interaction_t* blocks, int32_t num_blocks, float* const* filt,
+                                tsd_stream_t stream) {
+  TSD_REQUIRE(batch && edges && edge_attr && blocks && filt && num_blocks >= 1);
+  if (num_blocks > TSD_FS_MAX_LAYERS) return TSD_ERR_UNSUPPORTED;
+  const int H = blocks[0].nn2.out_features;
+  FilterStackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M_cap = batch->edge_capacity;
+  a.M_ptr = edges->num_edges;
+  a.H = H;
+  a.num_layers = num_blocks;
+  a.A = edge_attr;
+  a.len = edges->length;
+  for (int l = 0; l < num_blocks; ++l) {
+    const tsd_interaction_t& b = blocks[l];
+    if (b.nn0.in_features != H || b.nn0.out_features != H || b.nn2.in_features != H || b.nn2.out_features != H)
+      return TSD_ERR_UNSUPPORTED;
+    TSD_REQUIRE(filt[l]);
+    a.layer[l].W0 = b.nn0.weight;
+    a.layer[l].b0 = b.nn0.bias;
+    a.layer[l].W2 = b.nn2.weight;
+    a.layer[l].b2 = b.nn2.bias;
+    a.layer[l].cutoff = b.cutoff;
+    a.layer[l].smooth = b.smooth;
+    a.layer[l].out = filt[l];
+  }
+  return tsd_filter_stack_tf32(a, tsd_cu(stream));
+}
+
+// tuning hook of profiles/scripts (not part of the C-ABI header): -1 = one filter kernel per block (round-2 path),
+// 0 = all blocks in one launch, k > 0 = two launches, blocks [0, k) and [k, L)
+static int g_filter_stack_mode = -1;
+extern "C" void tsd_tune_filter_stack(int code) { g_filter_stack_mode = code; }
+
 // Whole SchNet encoder (schnet.py:203-225).  fp32 mode: one tsd_cfconv_layer per block.  tf32
 // mode: per block ONE chained filter-network kernel on the edges, the segmented aggregation, and
 // chained node kernels -- no (E,H) / (N,H) intermediate round trips.
@@ -568,26 +606,48 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     na.st[0].W = blocks[0].lin1.weight;
     na.st[0].store = x1buf[0];
     TSD_TRY(tsd_node_update_tf32(na, tile, side));
+    // With one filter buffer per block the filter networks of all blocks run as ONE kernel (filter_stack.cu) -- or as
+    // two launches, so that the node chain starts after the first few blocks' filters -- ahead of the node side.
+    bool stacked = g_filter_stack_mode >= 0 && nbuf >= num_blocks && num_blocks <= TSD_FS_MAX_LAYERS;
+    int stack_cut = 0;
+    if (stacked) {
+      stack_cut = g_filter_stack_mode > 0 && g_filter_stack_mode < num_blocks ? g_filter_stack_mode : num_blocks;
+      int rc = tsd_filter_stack(batch, edges, edge_attr, blocks, stack_cut, fbuf, stream);
+      if (rc == TSD_ERR_UNSUPPORTED) {
+        stacked = false;
+      } else {
+        TSD_TRY(rc);
+        TSD_CUDA(cudaEventRecord(fk.edge_done[0], s));
+        if (stack_cut < num_blocks) {
+          TSD_TRY(tsd_filter_stack(batch, edges, edge_attr, blocks + stack_cut, num_blocks - stack_cut, fbuf + stack_cut, stream));
+          TSD_CUDA(cudaEventRecord(fk.edge_done[stack_cut], s));
+        }
+      }
+    }
     for (int l = 0; l < num_blocks; ++l) {
       const tsd_interaction_t& b = blocks[l];
       float* filt = fbuf[l % nbuf];
-      if (l >= nbuf) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - nbuf], 0));  // buffer reuse: that block has read it
-      ChainArgs c;
-      memset(&c, 0, sizeof(c));
-      c.M_cap = batch->edge_capacity;
-      c.M_ptr = edges->num_edges;
-      c.H = H;
-      c.A = edge_attr;
-      c.num_stages = 2;
-      c.st[0] = chain_stage(b.nn0, TSD_ACT_SSP);
-      c.st[1] = chain_stage(b.nn2, TSD_ACT_NONE);
-      c.st[1].scale_len = edges->length;
-      c.st[1].cutoff = b.cutoff;
-      c.st[1].smooth = b.smooth;
-      c.st[1].store = filt;
-      TSD_TRY(tsd_chain_tf32(c, s));
-      TSD_CUDA(cudaEventRecord(fk.edge_done[l], s));
-      TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
+      if (stacked) {
+        if (l == 0 || l == stack_cut) TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
+      } else {
+        if (l >= nbuf) TSD_CUDA(cudaStreamWaitEvent(s, fk.agg_done[l - nbuf], 0));  // buffer reuse: that block has read it
+        ChainArgs c;
+        memset(&c, 0, sizeof(c));
+        c.M_cap = batch->edge_capacity;
+        c.M_ptr = edges->num_edges;
+        c.H = H;
+        c.A = edge_attr;
+        c.num_stages = 2;
+        c.st[0] = chain_stage(b.nn0, TSD_ACT_SSP);
+        c.st[1] = chain_stage(b.nn2, TSD_ACT_NONE);
+        c.st[1].scale_len = edges->length;
+        c.st[1].cutoff = b.cutoff;
+        c.st[1].smooth = b.smooth;
+        c.st[1].store = filt;
+        TSD_TRY(tsd_chain_tf32(c, s));
+        TSD_CUDA(cudaEventRecord(fk.edge_done[l], s));
+        TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[l], 0));
+      }
       memset(&na, 0, sizeof(na));
       na.num_nodes = batch->num_nodes;
       na.nodes_per_cluster = npc;

@@ -167,6 +167,27 @@ struct NodeArgs {
   NodeStage st[3];
 };
 
+// the CFConv filter networks of ALL interaction blocks on one 128-row tile, layer after layer (filter_stack.cu)
+constexpr int TSD_FS_MAX_LAYERS = 8;
+struct FilterStackLayer {
+  const float* W0;  // nn.0 weight (H, H), TF32-rounded shadow
+  const float* b0;  // (H) or NULL
+  const float* W2;  // nn.2 weight
+  const float* b2;
+  float cutoff;
+  int smooth;
+  float* out;       // (M_cap, H) filter of this block
+};
+struct FilterStackArgs {
+  int M_cap;
+  const int* M_ptr;
+  int H, num_layers;
+  const float* A;    // edge_attr (M_cap, H)
+  const float* len;  // (M_cap)
+  FilterStackLayer layer[TSD_FS_MAX_LAYERS];
+};
+int tsd_filter_stack_tf32(const FilterStackArgs& a, cudaStream_t stream);
+
 int tsd_node_tile(int num_nodes, int filter_tiles, int* nodes_per_cluster);  // node_update.cu: kernel shape
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream);
 int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream);           // gemm_chain.cu

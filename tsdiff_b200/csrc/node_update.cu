@@ -36,9 +36,13 @@ using namespace tc;
 // -DTSD_NODE_DBG: %globaltimer stamps of cluster 0's leader (profiles/scripts/node_timeline.py); off in the product build
 #ifdef TSD_NODE_DBG
 __device__ unsigned long long g_node_dbg[64];
-#define NU_STAMP(slot)                                              \
-  do {                                                              \
-    if (blockIdx.x == 0) g_node_dbg[slot] = gtimer();               \
+__device__ unsigned long long g_node_cta[256 * 4];  // per CTA: start, aggregation done, end, in-edges
+#define NU_STAMP(slot)                                                                         \
+  do {                                                                                         \
+    if (blockIdx.x == 0) g_node_dbg[slot] = gtimer();                                          \
+    if ((slot) == 0 && blockIdx.x < 256) g_node_cta[blockIdx.x * 4 + 0] = gtimer();            \
+    if ((slot) == 2 && blockIdx.x < 256) g_node_cta[blockIdx.x * 4 + 1] = gtimer();            \
+    if ((slot) == 6 && blockIdx.x < 256) g_node_cta[blockIdx.x * 4 + 2] = gtimer();            \
   } while (0)
 #else
 #define NU_STAMP(slot) do {} while (0)
@@ -52,37 +56,6 @@ constexpr int NU_SLOT_PANELS = 2;
 struct NodeMaps {
   CUtensorMap w[3];
 };
-
-template <int CW>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) {
-  static_assert(CW == 8 || CW == 16 || CW == 32, "column count per warp");
-  if constexpr (CW == 8) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-  } else if constexpr (CW == 16) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-  } else {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-  }
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __device__ __forceinline__ void nu_fma_rn4(float4& acc, const float4& x, const float4& w) {
   acc.x = __fadd_rn(acc.x, __fmul_rn(x.x, w.x));
@@ -309,6 +282,9 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
       for (int i = tid; i <= NA; i += NW) s_ptr[i] = p.in_ptr[min(node0 + my0 + i, N)];
       asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
       const int seg0 = s_ptr[0], seg_n = s_ptr[NA] - seg0;
+#ifdef TSD_NODE_DBG
+      if (tid == 0 && blockIdx.x < 256) g_node_cta[blockIdx.x * 4 + 3] = (unsigned long long)seg_n;
+#endif
       const bool staged = seg_n <= CAP;
       if (staged) {
         for (int i = tid; i < seg_n; i += NW) {
@@ -445,6 +421,7 @@ int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
 // stream (every CTA reads every W once) stays small against them.
 #ifdef TSD_NODE_DBG
 extern "C" void tsd_node_dbg_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_node_dbg, sizeof(g_node_dbg)); }
+extern "C" void tsd_node_cta_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_node_cta, sizeof(g_node_cta)); }
 #endif
 static int g_node_tile_override = 0;
 // tuning hook of profiles/scripts (not part of the C-ABI header): code = atoms per cluster * 10 + CTAs per cluster,

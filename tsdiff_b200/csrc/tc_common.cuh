@@ -52,6 +52,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// 2-D tiled TMA store shared -> global (bulk async-group of the issuing thread): the box is clipped to the tensor's
+// extent.  The issuing thread commits the group and waits for the shared-memory READS before the buffer is reused.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -87,6 +98,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// the same MMA with the A operand in TMEM: row m of A = TMEM lane m, element k = column (a_tmem + k), 32 bits each
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -106,10 +129,93 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// tcgen05.ld of CW (8 / 16 / 32) consecutive accumulator columns of this warp's TMEM lane quarter
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) {
+  static_assert(CW == 8 || CW == 16 || CW == 32, "column count per warp");
+  if constexpr (CW == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+  } else if constexpr (CW == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// the same load without the wait: the caller overlaps it with other work and calls tmem_wait_ld() before reading v
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols_async(uint32_t taddr, uint32_t (&v)[CW]) {
+  static_assert(CW == 8 || CW == 16, "column count per warp");
+  if constexpr (CW == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// registers -> CW consecutive TMEM columns of this warp's lane quarter (the A operand of a following tcgen05.mma)
+template <int CW>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[CW]) {
+  static_assert(CW == 8 || CW == 16, "column count per warp");
+  if constexpr (CW == 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // byte offset of the 16-byte chunk `c` (4 floats) of row `r` inside a K-major SW128 panel
 // (identical to what a SWIZZLE_128B tensor map writes for a [rows][32 float] box)
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// log(1 + exp(-a)), a >= 0: what __logf(1.f + __expf(-a)) computes (ex2.approx of a * -log2(e), lg2.approx times ln 2)
+// with the .ftz forms of the two SFU instructions.  exp(-a) in (0, 1] and 1 + exp(-a) in [1, 2], so flushing a
+// denormal exp(-a) to zero cannot change the sum; without .ftz every call carries two range checks and two rescaling
+// multiplies (FSETP + FMUL pairs) -- a third of the epilogue's instructions.
+__device__ __forceinline__ float tc_log1p_exp_neg(float a) {
+  float e, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * -1.4426950408889634f));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
+  return l * 0.693147182464599609375f;
 }
 
 // fast-math activations: this arithmetic mode already carries the TF32 bound, so the SFU
@@ -122,8 +228,8 @@ __device__ __forceinline__ float tc_act(float x) {
   // branch-free softplus: max(x,0) + log(1 + exp(-|x|)).  (Measured, profiles/r2_variants.txt: replacing the lg2 by an
   // FMA-pipe polynomial and the cvt.rna.tf32 by two ALU operations changed nothing -- the epilogues are bound by
   // instruction issue, not by the XU pipe.)
-  if (ACT == TSD_ACT_SSP) return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))) - TSD_SSP_SHIFT;
-  if (ACT == TSD_ACT_SOFTPLUS) return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
+  if (ACT == TSD_ACT_SSP) return fmaxf(x, 0.f) + tc_log1p_exp_neg(fabsf(x)) - TSD_SSP_SHIFT;
+  if (ACT == TSD_ACT_SOFTPLUS) return fmaxf(x, 0.f) + tc_log1p_exp_neg(fabsf(x));
   return x;
 }
 
