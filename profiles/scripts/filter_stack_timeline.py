@@ -15,6 +15,7 @@ class A: pass
 args = A(); args.batch = 100; args.network = 'condensenc'; args.math = 'tf32'; args.ld_steps = 5000
 dev = torch.device('cuda:0')
 lib = L.load()
+lib.tsd_tune_filter_stack(0)
 data = bench.build_inputs(args, 0)
 model, cfg = bench.make_models(args, dev)
 data_dev = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
@@ -27,7 +28,7 @@ torch.cuda.synchronize()
 buf = (C.c_ulonglong * 256)()
 lib.tsd_fs_dbg_read(buf)
 names = {0: 'epi  acc1 ready', 1: 'epi  X quarter 0', 2: 'epi  X quarter 1', 3: 'epi  X quarter 2', 4: 'epi  X quarter 3',
-         5: 'epi  acc2 ready', 6: 'epi  staged (tid 0)', 7: 'epi  all staged', 8: 'epi  TMA store read', 9: 'mma  A first panel',
+         5: 'st   acc2 ready', 6: 'st   acc2 read, stores issued', 7: '-', 8: 'st   last store read', 9: 'mma  A first panel',
          10: 'mma  A issued', 11: 'mma  X quarter 0 seen', 12: 'mma  B issued', 13: 'tma  layer first panel', 14: 'tma  A last panel',
          15: 'tma  B last panel'}
 t0 = min(v for v in buf if v)

@@ -9,9 +9,15 @@ class A: pass
 args = A(); args.batch = 100; args.network = sys.argv[2] if len(sys.argv) > 2 else 'condensenc'; args.math = sys.argv[1] if len(sys.argv) > 1 else 'tf32'; args.ld_steps = 5000
 dev = torch.device('cuda:0')
 import os
+from tsdiff_b200 import _lib as L
 if os.environ.get('NODE_TILE'):
-    from tsdiff_b200 import _lib as L
     L.load().tsd_tune_node_tile(int(os.environ['NODE_TILE']))
+if os.environ.get('STACK_MODE'):
+    L.load().tsd_tune_filter_stack(int(os.environ['STACK_MODE']))
+if os.environ.get('STACK_CTAS'):
+    L.load().tsd_tune_filter_stack_grid(int(os.environ['STACK_CTAS']))
+if os.environ.get('NODE_PDL'):
+    L.load().tsd_tune_node_pdl(int(os.environ['NODE_PDL']))
 data = bench.build_inputs(args, 0)
 model, cfg = bench.make_models(args, dev)
 data_dev = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}

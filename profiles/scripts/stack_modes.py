@@ -1,6 +1,6 @@
 """Langevin-step time (CUDA-graph replays, late-trajectory edge count) for the filter-stack launch modes and node tiles
 in ONE process: the tuning hooks are run-time switches, every mode re-captures its graph.
-usage: python profiles/scripts/stack_modes.py [mode:tile:splitmma ...]   (mode -1 = one filter kernel per block)"""
+usage: python profiles/scripts/stack_modes.py [mode:tile[:pdl[:stack_ctas]] ...]   (mode -1 = one filter kernel per block)"""
 import sys, json, torch
 sys.path.insert(0, '.')
 import bench
@@ -13,13 +13,16 @@ lib = L.load()
 data = bench.build_inputs(args, 0)
 model, cfg = bench.make_models(args, dev)
 dd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
-specs = sys.argv[1:] or ["-1:0:0", "0:0:0"]
+specs = sys.argv[1:] or ["-1:0", "0:0"]
 ref_pos = None
 for spec in specs:
-    mode, tile, split = (int(x) for x in spec.split(":"))
+    f = [int(x) for x in spec.split(":")]
+    mode, tile, pdl = f[0], f[1], (f[2] if len(f) > 2 else 1)
+    lib.tsd_tune_node_pdl(pdl)
+    grid = f[3] if len(f) > 3 else 0
+    lib.tsd_tune_filter_stack_grid(grid)
     lib.tsd_tune_filter_stack(mode)
     lib.tsd_tune_node_tile(tile)
-    lib.tsd_tune_filter_stack_mma(split)
     torch.manual_seed(0)
     eng, runner = bench.build_runner(args, [model], dd, keep_traj=False)
     runner.prepare(); runner.run(n_steps=1500); torch.cuda.synchronize()
@@ -28,7 +31,7 @@ for spec in specs:
     t0.record()
     for _ in range(1500): runner.graph.replay()
     t1.record(); torch.cuda.synchronize()
-    out = {"mode": mode, "tile": tile, "split_mma": split, "step_us": t0.elapsed_time(t1) / 1500 * 1e3,
+    out = {"mode": mode, "tile": tile, "pdl": pdl, "stack_ctas": grid, "step_us": t0.elapsed_time(t1) / 1500 * 1e3,
            "pairs": eng.plan.work_count()}
     if pos is not None:
         if ref_pos is None: ref_pos = pos

@@ -385,7 +385,7 @@ extern "C" int tsd_interaction_node_update(const tsd_batch_t* batch, const tsd_e
   NodeArgs na;
   memset(&na, 0, sizeof(na));
   int npc = 0;
-  const int tile = tsd_node_tile(batch->num_nodes, tsd_ceil_div(batch->edge_capacity, 128), &npc);
+  const int tile = tsd_node_tile(true, &npc);  // a single launch has the GPU to itself
   na.num_nodes = batch->num_nodes;
   na.nodes_per_cluster = npc;
   na.H = H;
@@ -526,7 +526,7 @@ extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edg
 
 // tuning hook of profiles/scripts (not part of the C-ABI header): -1 = one filter kernel per block (round-2 path),
 // 0 = all blocks in one launch, k > 0 = two launches, blocks [0, k) and [k, L)
-static int g_filter_stack_mode = -1;
+static int g_filter_stack_mode = 0;
 extern "C" void tsd_tune_filter_stack(int code) { g_filter_stack_mode = code; }
 
 // Whole SchNet encoder (schnet.py:203-225).  fp32 mode: one tsd_cfconv_layer per block.  tf32
@@ -584,7 +584,6 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     // (node_update.cu).  x1 ping-pongs between nf0 and nf1: a CTA's aggregation gathers x1 rows of atoms
     // that other CTAs own, so the next block's x1 must not overwrite them.
     int npc = 0;
-    const int tile = tsd_node_tile(batch->num_nodes, tsd_ceil_div(batch->edge_capacity, 128), &npc);
     float* x1buf[2] = {nf0, nf1};
     // filter buffers: ef1, ef0, then the optional pool (one per block lets every filter kernel run ahead)
     float* fbuf[EncoderFork::MAX_BLOCKS];
@@ -605,7 +604,6 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     na.num_stages = 1;
     na.st[0].W = blocks[0].lin1.weight;
     na.st[0].store = x1buf[0];
-    TSD_TRY(tsd_node_update_tf32(na, tile, side));
     // With one filter buffer per block the filter networks of all blocks run as ONE kernel (filter_stack.cu) -- or as
     // two launches, so that the node chain starts after the first few blocks' filters -- ahead of the node side.
     bool stacked = g_filter_stack_mode >= 0 && nbuf >= num_blocks && num_blocks <= TSD_FS_MAX_LAYERS;
@@ -624,6 +622,10 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
         }
       }
     }
+    // Node kernel shape: behind the filter stack the node chain has the GPU to itself, so two CTAs share a 32-atom tile's
+    // gathers; next to per-block filter kernels one CTA per tile competes least for SMs (profiles/r3_stack_modes.txt).
+    const int tile = tsd_node_tile(stacked && stack_cut == num_blocks, &npc);
+    TSD_TRY(tsd_node_update_tf32(na, tsd_node_tile(false, &npc), side));  // x1 of block 0: a dense input, no gathers
     for (int l = 0; l < num_blocks; ++l) {
       const tsd_interaction_t& b = blocks[l];
       float* filt = fbuf[l % nbuf];

@@ -14,13 +14,22 @@
 //                M128 x N256 x K8 tf32 MMA of streamed W -- the ring must never drain.
 //   warp 17      MMA issuer: acc1 = A . W0^T (TMEM columns [0,H)), then acc2 = X . W2^T (columns [H,2H))
 //                panel by panel as soon as the epilogue warps have produced the matching QUARTER of X.
-//   warps 0..15  epilogues.  epi1: acc1 -> + b0 -> shifted softplus -> TF32 (RNE) -> X in the UMMA K-major
-//                SWIZZLE_128B layout (shared memory), handed to the MMA issuer in four column quarters, so
-//                the second GEMM trails the activation by a quarter instead of waiting for all of it.
-//                epi2: acc2 -> + b2 -> * C(len) -> staged in the same buffer (idle by then) -> TMA store;
-//                it overlaps the NEXT layer's first GEMM.
+//   warps 0..15  epilogues.  epi1: acc1 -> + b0 -> shifted softplus -> TF32 (RNE) -> written back IN PLACE over
+//                acc1 (tcgen05.st): X never leaves tensor memory, the second GEMM takes its A operand from
+//                TMEM.  Handed to the MMA issuer in four column quarters, so the second GEMM trails the
+//                activation by a quarter instead of waiting for all of it.
+//   warps 18..25 epi2 (two warps per TMEM lane quarter = 32 rows, even / odd output panels): acc2 -> + b2 -> * C(len)
+//                -> 32 x 32 block in the warp's own 4 KiB staging -> TMA store (1.2 us per block: the stores queue
+//                behind the weight loads of the same SM; reading the block back and storing whole 128-byte lines
+//                with st.global measured slower still, 1.75 us per block:
+//                profiles/r3_filter_stack_timeline_{tma_store,st_global}.txt).  No CTA-level barrier anywhere; it
+//                overlaps the NEXT layer's first GEMM and activation (the MMA issuer waits on `acc2_free`
+//                before it overwrites acc2).
 //
-// Shared memory (H = 256): X / staging 128 KiB + 2 ring slots x 48 KiB; TMEM: all 512 columns.
+// Shared memory (H = 256): 4 ring slots x 48 KiB + 8 x 4 KiB staging (the ring depth is what the weight
+// stream's throughput hangs on: with X in shared memory there was room for 2 slots = 96 KiB in flight and the
+// stream reached 61 of the 127 GB/s one SM can ingest; profiles/r3_filter_stack_timeline_smemX.txt).
+// TMEM: all 512 columns.
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -41,8 +50,11 @@ __device__ unsigned long long g_fs_dbg[256];
 
 constexpr int FS_EPI_WARPS = 16;
 constexpr int FS_EPI_THREADS = FS_EPI_WARPS * 32;
-constexpr int FS_THREADS = (FS_EPI_WARPS + 2) * 32;
+constexpr int FS_STORE_WARPS = 8;
+constexpr int FS_THREADS = (FS_EPI_WARPS + 2 + FS_STORE_WARPS) * 32;
+constexpr int FS_STAGE_BYTES = FS_STORE_WARPS * 32 * TC_BK * 4;  // per store warp 32 rows x 128 B
 constexpr int FS_MAX_SLOTS = 6;
+int g_fs_grid = 0;  // tuning hook of profiles/scripts: CTA count (0 = one per SM)
 
 struct FilterStackMaps {
   CUtensorMap a;
@@ -68,67 +80,52 @@ struct FsArgsDev {
 struct FsBars {
   uint64_t full[FS_MAX_SLOTS];
   uint64_t empty[FS_MAX_SLOTS];
-  uint64_t acc1_full, acc2_full;
+  uint64_t acc1_full, acc2_full, acc2_free;
   uint64_t x_ready[4];
   uint32_t tmem_base;
 };
 
-// CQ accumulator columns of one row: + bias, activation / scale, into the SW128 panel buffer
-template <int CQ, bool SSP>
-__device__ __forceinline__ void fs_columns(uint32_t taddr, const float* __restrict__ bias, int c0, float scale, bool valid,
-                                           uint8_t* xbuf, int row) {
+// epi1: CQ accumulator columns of this thread's row -> + bias -> shifted softplus -> TF32 (RNE), written back over
+// the same TMEM columns: the A operand of the second GEMM
+template <int CQ>
+__device__ __forceinline__ void fs_activate_in_place(uint32_t taddr, const float* __restrict__ bias) {
   float4 b[CQ / 4];
 #pragma unroll
   for (int j = 0; j < CQ / 4; ++j)
-    b[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t v[CQ];
-  tmem_ld_cols<CQ>(taddr + (uint32_t)c0, v);
-  uint8_t* panel = xbuf + (size_t)(c0 >> 5) * TC_A_PANEL_BYTES;
-  const int cb = (c0 & 31) >> 2;
+  tmem_ld_cols<CQ>(taddr, v);
 #pragma unroll
   for (int j = 0; j < CQ / 4; ++j) {
-    float4 o = make_float4(__uint_as_float(v[4 * j + 0]) + b[j].x, __uint_as_float(v[4 * j + 1]) + b[j].y,
-                           __uint_as_float(v[4 * j + 2]) + b[j].z, __uint_as_float(v[4 * j + 3]) + b[j].w);
-    if (SSP) {
-      o = tf32_rn4(make_float4(tc_act<TSD_ACT_SSP>(o.x), tc_act<TSD_ACT_SSP>(o.y), tc_act<TSD_ACT_SSP>(o.z),
-                               tc_act<TSD_ACT_SSP>(o.w)));
-    } else {
-      o = valid ? make_float4(o.x * scale, o.y * scale, o.z * scale, o.w * scale) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    *reinterpret_cast<float4*>(panel + sw128_off(row, cb + j)) = o;
+    v[4 * j + 0] = __float_as_uint(tf32_rn(tc_act<TSD_ACT_SSP>(__uint_as_float(v[4 * j + 0]) + b[j].x)));
+    v[4 * j + 1] = __float_as_uint(tf32_rn(tc_act<TSD_ACT_SSP>(__uint_as_float(v[4 * j + 1]) + b[j].y)));
+    v[4 * j + 2] = __float_as_uint(tf32_rn(tc_act<TSD_ACT_SSP>(__uint_as_float(v[4 * j + 2]) + b[j].z)));
+    v[4 * j + 3] = __float_as_uint(tf32_rn(tc_act<TSD_ACT_SSP>(__uint_as_float(v[4 * j + 3]) + b[j].w)));
   }
+  tmem_st_cols<CQ>(taddr, v);
 }
 
-// SPLIT: every K step as two N = H/2 MMAs on disjoint accumulator columns (consecutive MMAs into the SAME accumulator
-// serialise: 171 instead of 128 clk per M128 x N256 x K8, profiles/r2_umma_small_n.txt) at the price of reading the
-// A-side panel twice from shared memory.
-template <int H, bool SPLIT>
-__device__ __forceinline__ void fs_mma_panel(uint32_t acc, uint32_t a_addr, uint32_t w_addr, uint32_t idesc, bool first) {
-  const uint64_t adesc = umma_desc_sw128(a_addr);
-  if (!SPLIT) {
-    const uint64_t bdesc = umma_desc_sw128(w_addr);
+// one K panel (32 floats = 4 MMAs of K = 8) of the first GEMM: A = the tile's edge_attr panel, B = the W0 panel (shared memory)
+__device__ __forceinline__ void fs_mma_panel_ss(uint32_t acc, uint32_t a_addr, uint32_t w_addr, uint32_t idesc, bool first) {
+  const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(w_addr);
 #pragma unroll
-    for (int kk = 0; kk < TC_BK / 8; ++kk)
-      umma_tf32(acc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (!first || kk != 0) ? 1u : 0u);
-  } else {
-    const uint64_t bdesc0 = umma_desc_sw128(w_addr);
-    const uint64_t bdesc1 = umma_desc_sw128(w_addr + (uint32_t)(H / 2) * 128u);
+  for (int kk = 0; kk < TC_BK / 8; ++kk)
+    umma_tf32(acc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (!first || kk != 0) ? 1u : 0u);
+}
+// ... of the second GEMM: A = 32 TMEM columns of X (row m = lane m, one 32-bit column per K element), B = the W2 panel
+__device__ __forceinline__ void fs_mma_panel_ts(uint32_t acc, uint32_t x_tmem, uint32_t w_addr, uint32_t idesc, bool first) {
+  const uint64_t bdesc = umma_desc_sw128(w_addr);
 #pragma unroll
-    for (int kk = 0; kk < TC_BK / 8; ++kk) {
-      umma_tf32(acc, adesc + (uint64_t)(2 * kk), bdesc0 + (uint64_t)(2 * kk), idesc, (!first || kk != 0) ? 1u : 0u);
-      umma_tf32(acc + (uint32_t)(H / 2), adesc + (uint64_t)(2 * kk), bdesc1 + (uint64_t)(2 * kk), idesc,
-                (!first || kk != 0) ? 1u : 0u);
-    }
-  }
+  for (int kk = 0; kk < TC_BK / 8; ++kk)
+    umma_tf32_ts(acc, x_tmem + (uint32_t)(8 * kk), bdesc + (uint64_t)(2 * kk), idesc, (!first || kk != 0) ? 1u : 0u);
 }
 
-template <int H, bool SPLIT>
+template <int H>
 __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev p, const __grid_constant__ FilterStackMaps maps,
                                                                 int num_slots) {
-  constexpr int NKB = H / TC_BK;                 // K panels per GEMM
+  constexpr int NKB = H / TC_BK;                 // K panels per GEMM = 32-column panels of the output
   constexpr int W_PANEL = H * TC_BK * 4;         // bytes of one W panel: H rows x 128 B
   constexpr int SLOT = W_PANEL + TC_A_PANEL_BYTES;
-  constexpr int X_BYTES = NKB * TC_A_PANEL_BYTES;
   constexpr int CQ = H / 16;                     // accumulator columns per epilogue warp and quarter
   constexpr int KBQ = NKB / 4;                   // K panels per quarter of X
   static_assert(NKB % 4 == 0 && (CQ == 8 || CQ == 16), "H must be 128 or 256");
@@ -136,15 +133,18 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M_ptr ? min(*p.M_ptr, p.M_cap) : p.M_cap;
-  const int m0 = blockIdx.x * TC_BM;
-  if (m0 >= M) return;
+  // Work items = (layer, 128-row tile), layer-major; CTA b takes items b, b + gridDim.x, ...  A tile's layers are
+  // independent of each other (each reads edge_attr again), so the items spread over ALL SMs whatever the tile count.
+  const int tiles = (M + TC_BM - 1) / TC_BM;
+  const int items = tiles * p.num_layers;
+  const int stride = (int)gridDim.x;
+  if ((int)blockIdx.x >= items) return;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  uint8_t* xbuf = smem_gen;
-  uint8_t* ring = smem_gen + X_BYTES;
-  const uint32_t ring_base = smem_base + X_BYTES;
+  uint8_t* stage = smem_gen;                     // per store warp 32 rows x 32 floats, SWIZZLE_128B
+  uint8_t* ring = smem_gen + FS_STAGE_BYTES;
+  const uint32_t ring_base = smem_base + FS_STAGE_BYTES;
   FsBars* bars = reinterpret_cast<FsBars*>(ring + (size_t)num_slots * SLOT);
-  const int L = p.num_layers;
 
   if (tid == 0) {
     for (int s = 0; s < num_slots; ++s) {
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
     }
     mbar_init(&bars->acc1_full, 1);
     mbar_init(&bars->acc2_full, 1);
+    mbar_init(&bars->acc2_free, FS_STORE_WARPS);
     for (int t = 0; t < 4; ++t) mbar_init(&bars->x_ready[t], FS_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a)) : "memory");
@@ -174,10 +175,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int g = 0;
-      for (int l = 0; l < L; ++l) {
+      for (int item = blockIdx.x; item < items; item += stride) {
+        const int l = item / tiles, m0 = (item - l * tiles) * TC_BM;
         for (int st = 0; st < 2; ++st) {
           const CUtensorMap* wmap = &maps.w[2 * l + st];
-          if (g + NKB < 2 * L * NKB) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(wmap + 1)) : "memory");
+          if (st == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(wmap + 1)) : "memory");
+          else if (item + stride < items)
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[2 * ((item + stride) / tiles)])) : "memory");
           for (int kb = 0; kb < NKB; ++kb, ++g) {
             const int s = g % num_slots, round = g / num_slots;
             if (round > 0) mbar_wait(&bars->empty[s], (uint32_t)((round - 1) & 1));
@@ -194,84 +198,112 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
   } else if (warp == FS_EPI_WARPS + 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(SPLIT ? H / 2 : H);
-      int g = 0;
-      for (int l = 0; l < L; ++l) {
-        // acc1 = A . W0^T.  acc1 is free: the last quarter of X of the previous layer (waited on below) is signalled
-        // after every epilogue thread's last read of it.
+      const uint32_t idesc = umma_idesc_tf32(H);
+      int g = 0, it = 0;
+      for (int item = blockIdx.x; item < items; item += stride, ++it) {
+        const int l = item / tiles;
+        (void)l;
+        // acc1 = A . W0^T.  acc1 (= the previous layer's X) is free: the MMAs of one thread execute in issue order, so
+        // these follow the previous layer's second GEMM, the only reader of X.
         for (int kb = 0; kb < NKB; ++kb, ++g) {
           const int s = g % num_slots, round = g / num_slots;
           mbar_wait(&bars->full[s], (uint32_t)(round & 1));
           tc_fence_after();
           if (kb == 0) FS_STAMP(16 * l + 9);
           const uint32_t slot = ring_base + (uint32_t)(s * SLOT);
-          fs_mma_panel<H, SPLIT>(acc1, slot + (uint32_t)W_PANEL, slot, idesc, kb == 0);
+          fs_mma_panel_ss(acc1, slot + (uint32_t)W_PANEL, slot, idesc, kb == 0);
           umma_commit(&bars->empty[s]);
         }
         umma_commit(&bars->acc1_full);
         FS_STAMP(16 * l + 10);
-        // acc2 = X . W2^T, a quarter of X (KBQ panels) at a time.  acc2 is free: x_ready[0] of THIS layer needs every
-        // epilogue thread's arrival, which comes after its reads of the previous layer's acc2.
+        // acc2 = X . W2^T, a quarter of X (KBQ panels) at a time, once the store warps have read the previous layer's acc2
+        if (it > 0) {
+          mbar_wait(&bars->acc2_free, (uint32_t)((it - 1) & 1));
+          tc_fence_after();
+        }
         for (int kb = 0; kb < NKB; ++kb, ++g) {
           if (kb % KBQ == 0) {
-            mbar_wait(&bars->x_ready[kb / KBQ], (uint32_t)(l & 1));
+            mbar_wait(&bars->x_ready[kb / KBQ], (uint32_t)(it & 1));
             tc_fence_after();
             if (kb == 0) FS_STAMP(16 * l + 11);
           }
           const int s = g % num_slots, round = g / num_slots;
           mbar_wait(&bars->full[s], (uint32_t)(round & 1));
           tc_fence_after();
-          fs_mma_panel<H, SPLIT>(acc2, smem_base + (uint32_t)(kb * TC_A_PANEL_BYTES), ring_base + (uint32_t)(s * SLOT), idesc,
-                                 kb == 0);
+          fs_mma_panel_ts(acc2, acc1 + (uint32_t)(kb * TC_BK), ring_base + (uint32_t)(s * SLOT), idesc, kb == 0);
           umma_commit(&bars->empty[s]);
         }
         umma_commit(&bars->acc2_full);
         FS_STAMP(16 * l + 12);
       }
     }
-  } else {
-    // ---------------------------------------------------------------- epilogue warps
-    const int q = warp & 3, cg = warp >> 2;  // TMEM lane quarter (hardware: warp id % 4), column group within a quarter
-    const int row = q * 32 + lane;
-    const bool valid = m0 + row < M;
-    const float len = p.len[min(m0 + row, M - 1)];
+  } else if (warp < FS_EPI_WARPS) {
+    // ---------------------------------------------------------------- activation warps (epi1)
+    const int q = warp & 3, cg = warp >> 2;  // TMEM lane quarter (hardware: warp id % 4), column group
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    for (int l = 0; l < L; ++l) {
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += stride, ++it) {
+      const int l = item / tiles;
       const float* const b0 = p.layer[l].b0;
-      const float* const b2 = p.layer[l].b2;
-      const float cscale = tsd_cutoff_fn(len, p.layer[l].cutoff, p.layer[l].smooth);
-      // epi1: X = tf32(ssp(acc1 + b0)).  X is free: the previous layer's second GEMM has retired (acc2_full was waited
-      // on in epi2) and its staged output has been read by the TMA store (named barrier below).
-      mbar_wait(&bars->acc1_full, (uint32_t)(l & 1));
+      // X = tf32(ssp(acc1 + b0)), in place, quarter by quarter
+      mbar_wait(&bars->acc1_full, (uint32_t)(it & 1));
       tc_fence_after();
       if (tid == 0) FS_STAMP(16 * l + 0);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        fs_columns<CQ, true>(acc1 + lane_addr, b0, t * (H / 4) + cg * CQ, 1.f, true, xbuf, row);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+        const int c0 = t * (H / 4) + cg * CQ;
+        fs_activate_in_place<CQ>(acc1 + lane_addr + (uint32_t)c0, b0 ? b0 + c0 : nullptr);
+        tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->x_ready[t]);
         if (tid == 0) FS_STAMP(16 * l + 1 + t);
       }
-      // epi2: filt = (acc2 + b2) * C(len), staged in X's buffer, stored by TMA
-      mbar_wait(&bars->acc2_full, (uint32_t)(l & 1));
-      tc_fence_after();
-      if (tid == 0) FS_STAMP(16 * l + 5);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) fs_columns<CQ, false>(acc2 + lane_addr, b2, t * (H / 4) + cg * CQ, cscale, valid, xbuf, row);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA store reads
-      if (tid == 0) FS_STAMP(16 * l + 6);
-      asm volatile("bar.sync 1, %0;" ::"r"(FS_EPI_THREADS) : "memory");
-      if (tid == 0) {
-        FS_STAMP(16 * l + 7);
-#pragma unroll 1
-        for (int kb = 0; kb < NKB; ++kb) tma_store_2d(&maps.out[l], xbuf + (size_t)kb * TC_A_PANEL_BYTES, kb * TC_BK, m0);
-        tma_store_commit();
-        tma_store_wait_read();
-        FS_STAMP(16 * l + 8);
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(FS_EPI_THREADS) : "memory");
     }
+  } else {
+    // ---------------------------------------------------------------- store warps (epi2)
+    const int q = warp & 3;  // TMEM lane quarter = rows [32 q, 32 q + 32) of the tile
+    const bool stamp = warp == FS_EPI_WARPS + 2 && lane == 0;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint8_t* const buf = stage + (size_t)(warp - (FS_EPI_WARPS + 2)) * (32 * TC_BK * 4);
+    const int kb0 = (warp - (FS_EPI_WARPS + 2)) >> 2;  // this warp's panels: kb0, kb0 + 2, ...
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += stride, ++it) {
+      const int l = item / tiles, m0 = (item - l * tiles) * TC_BM;
+      const float* const b2 = p.layer[l].b2;
+      const bool valid = m0 + row < M;
+      const float cscale = valid ? tsd_cutoff_fn(p.len[min(m0 + row, M - 1)], p.layer[l].cutoff, p.layer[l].smooth) : 0.f;
+      mbar_wait(&bars->acc2_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      if (stamp) FS_STAMP(16 * l + 5);
+#pragma unroll 1
+      for (int kb = kb0; kb < NKB; kb += FS_STORE_WARPS / 4) {
+        uint32_t v[32];
+        tmem_ld32(acc2 + lane_addr + (uint32_t)(kb * TC_BK), v);
+        if (lane == 0) tma_store_wait_read();  // this warp's previous store has read the staging block
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < TC_BK / 4; ++c) {
+          const float4 b = b2 ? __ldg(reinterpret_cast<const float4*>(b2 + kb * TC_BK + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 o = make_float4((__uint_as_float(v[4 * c + 0]) + b.x) * cscale, (__uint_as_float(v[4 * c + 1]) + b.y) * cscale,
+                                 (__uint_as_float(v[4 * c + 2]) + b.z) * cscale, (__uint_as_float(v[4 * c + 3]) + b.w) * cscale);
+          if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(buf + sw128_off(lane, c)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA store reads
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&maps.out[l], buf, kb * TC_BK, m0 + q * 32);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();  // this warp's acc2 reads precede the MMA issuer's next writes
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc2_free);
+      if (stamp) FS_STAMP(16 * l + 6);
+    }
+    if (lane == 0) tma_store_wait_read();  // the staging buffers outlive the last stores' reads
+    if (stamp) FS_STAMP(16 * (p.num_layers - 1) + 8);
   }
   __syncwarp();
   tc_fence_before();
@@ -281,20 +313,29 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
   }
 }
 
-template <int H, bool SPLIT>
+template <int H>
 int fs_launch(const FsArgsDev& d, const FilterStackMaps& maps, cudaStream_t stream) {
-  constexpr int SLOT = H * TC_BK * 4 + TC_A_PANEL_BYTES, X_BYTES = (H / TC_BK) * TC_A_PANEL_BYTES;
-  const int budget = 227 * 1024 - 1024 - X_BYTES - 256;  // alignment slack, barriers
+  constexpr int SLOT = H * TC_BK * 4 + TC_A_PANEL_BYTES;
+  const int budget = 227 * 1024 - 1024 - FS_STAGE_BYTES - 256;  // alignment slack, staging, barriers
   int slots = budget / SLOT;
   if (slots > FS_MAX_SLOTS) slots = FS_MAX_SLOTS;
   if (slots < 2) return TSD_ERR_UNSUPPORTED;
-  const size_t smem = 1024 + (size_t)X_BYTES + (size_t)slots * SLOT + 256;
+  const size_t smem = 1024 + (size_t)FS_STAGE_BYTES + (size_t)slots * SLOT + 256;
   static size_t attr_smem = 0;  // per instantiation
   if (smem > attr_smem) {
-    TSD_CUDA(cudaFuncSetAttribute(k_filter_stack<H, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSD_CUDA(cudaFuncSetAttribute(k_filter_stack<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  k_filter_stack<H, SPLIT><<<dim3(tsd_ceil_div(d.M_cap, TC_BM)), dim3(FS_THREADS), smem, stream>>>(d, maps, slots);
+  // one CTA per SM (the shared memory allows no more), never more CTAs than work items of the largest possible pair count
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    TSD_CUDA(cudaGetDevice(&dev));
+    TSD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int max_items = tsd_ceil_div(d.M_cap, TC_BM) * d.num_layers;
+  const int grid = g_fs_grid > 0 ? g_fs_grid : (max_items < num_sms ? max_items : num_sms);
+  k_filter_stack<H><<<dim3(grid), dim3(FS_THREADS), smem, stream>>>(d, maps, slots);
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }
@@ -304,9 +345,7 @@ int fs_launch(const FsArgsDev& d, const FilterStackMaps& maps, cudaStream_t stre
 #ifdef TSD_FS_DBG
 extern "C" void tsd_fs_dbg_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_fs_dbg, sizeof(g_fs_dbg)); }
 #endif
-static int g_fs_split_mma = 0;
-// tuning hook of profiles/scripts (not part of the C-ABI header): 1 = two N/2 MMAs per K step
-extern "C" void tsd_tune_filter_stack_mma(int split) { g_fs_split_mma = split; }
+extern "C" void tsd_tune_filter_stack_grid(int ctas) { g_fs_grid = ctas; }
 
 int tsd_filter_stack_tf32(const FilterStackArgs& a, cudaStream_t stream) {
   using namespace tc;
@@ -331,13 +370,12 @@ int tsd_filter_stack_tf32(const FilterStackArgs& a, cudaStream_t stream) {
       return TSD_ERR_UNSUPPORTED;
     if (!make_tensor_map(&maps.w[2 * l], y.W0, (uint64_t)a.H, (uint64_t)a.H, (uint32_t)a.H) ||
         !make_tensor_map(&maps.w[2 * l + 1], y.W2, (uint64_t)a.H, (uint64_t)a.H, (uint32_t)a.H) ||
-        !make_tensor_map(&maps.out[l], y.out, (uint64_t)a.M_cap, (uint64_t)a.H, TC_BM))
+        !make_tensor_map(&maps.out[l], y.out, (uint64_t)a.M_cap, (uint64_t)a.H, 32))  // one store warp's block
       return TSD_ERR_UNSUPPORTED;
     d.layer[l].b0 = y.b0;
     d.layer[l].b2 = y.b2;
     d.layer[l].cutoff = y.cutoff;
     d.layer[l].smooth = y.smooth;
   }
-  if (a.H == 256) return g_fs_split_mma ? fs_launch<256, true>(d, maps, stream) : fs_launch<256, false>(d, maps, stream);
-  return g_fs_split_mma ? fs_launch<128, true>(d, maps, stream) : fs_launch<128, false>(d, maps, stream);
+  return a.H == 256 ? fs_launch<256>(d, maps, stream) : fs_launch<128>(d, maps, stream);
 }

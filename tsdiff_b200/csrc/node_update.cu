@@ -137,6 +137,9 @@ __device__ __forceinline__ void nu_wait_cluster(uint64_t* bar, uint32_t parity) 
   }
 }
 
+// tuning hook of profiles/scripts (not part of the C-ABI header): programmatic dependent launch of the node chain
+int g_node_pdl = 1;
+
 constexpr int NU_STAGE_BYTES = 16 * 1024;  // staged in-CSR ids of a CTA's atoms: 2 x 2048 entries
 
 // One cluster of C CTAs owns NT atoms.  Every CTA aggregates NT / C of them (the gathers want many SMs) and
@@ -268,6 +271,10 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_update(const NodeArgs p,
     }
   } else {
     // ------------------------------------------------------------------ workers
+    // Programmatic dependent launch: everything above (barriers, TMEM, the weight stream -- weights are written by no
+    // kernel of the step) ran while the previous node kernel was still finishing; the atoms' data is read from here on.
+    pdl_wait();
+    pdl_trigger();
     // (1) this CTA's NA rows of the stage-0 B operand -> the leader's xbuf
     constexpr int SL = H / 128;          // 128-channel slabs per atom
     constexpr int ITEMS = NA * SL;
@@ -403,13 +410,15 @@ int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
   cfg.blockDim = dim3(NU_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_node_pdl ? 2 : 1;
   TSD_CUDA(cudaLaunchKernelEx(&cfg, k_node_update<H, NT, C>, a, maps, slots, tmem_cols));
   TSD_LAUNCH_CHECK();
   return TSD_OK;
@@ -423,24 +432,22 @@ int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
 extern "C" void tsd_node_dbg_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_node_dbg, sizeof(g_node_dbg)); }
 extern "C" void tsd_node_cta_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_node_cta, sizeof(g_node_cta)); }
 #endif
+extern "C" void tsd_tune_node_pdl(int on) { g_node_pdl = on; }
 static int g_node_tile_override = 0;
 // tuning hook of profiles/scripts (not part of the C-ABI header): code = atoms per cluster * 10 + CTAs per cluster,
 // 0 restores the built-in choice
 extern "C" void tsd_tune_node_tile(int code) { g_node_tile_override = code; }
 
 // Kernel shape (atoms per cluster * 10 + CTAs per cluster) and the atoms a cluster really takes (0 = all of the shape).
-// 32 atoms per single CTA measured best at batch 100 (profiles/r2_variants_*.txt): fewer atoms per CTA shorten the
+// Measured at batch 100 (profiles/r2_variants_*.txt, profiles/r3_stack_modes.txt): fewer atoms per CTA shorten the
 // aggregation phase (bound by one SM's L2 ingest, 127 GB/s) but multiply the weight streams and the CTAs that compete
-// with the concurrently running filter kernels for SMs; more atoms per CTA (48, 64) or cluster variants that hand the
-// rows to a leader CTA lengthen the serial node chain.  Sizing the tile so that node + filter CTAs exactly fit the 148
-// SMs (tried: atoms per CTA derived from the edge capacity) only pays when the edge count is far below its capacity,
-// which a trained model's late trajectory is not (every pair inside the cutoff: 132 filter tiles at batch 100).
-int tsd_node_tile(int num_nodes, int filter_tiles, int* nodes_per_cluster) {
-  (void)num_nodes;
-  (void)filter_tiles;
+// with concurrently running filter kernels for SMs; more atoms per CTA (48, 64) lengthen the serial node chain.  Next to
+// per-block filter kernels one CTA per 32 atoms is best; when the node chain runs alone (behind the filter stack) a
+// cluster of two CTAs that share the gathers of a 32-atom tile is (the second CTA exits after its half).
+int tsd_node_tile(bool alone, int* nodes_per_cluster) {
   *nodes_per_cluster = 0;
   if (g_node_tile_override > 0) return g_node_tile_override;
-  return 321;
+  return alone ? 322 : 321;
 }
 
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
