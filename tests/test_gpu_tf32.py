@@ -192,11 +192,14 @@ def test_stress_shape_tf32_asymmetric_pairs_and_ld():
     assert (traj["tf32"] - traj["fp32"]).abs().max() < 1e-2
 
 
-@pytest.mark.parametrize("h,last", [(256, False), (256, True), (128, False)])
-def test_interaction_node_update_kernel_vs_fp64(h, last, syn4):
-    """k_node_update alone (the fused CFConv aggregation + transposed tcgen05 node linears) against an fp64 torch
-    evaluation of the same operator on a replicated golden graph (N = 1024 atoms, ragged last tile): h_out and x1_next
-    within the single-GEMM tf32 bound (1.5e-3 L2-relative); the aggregation inside is exact in fp32 before rounding."""
+@pytest.mark.parametrize("h,last,tile", [(256, False, 0), (256, True, 0), (128, False, 0), (256, False, 321), (256, False, 323),
+                                         (256, True, 323), (128, False, 323), (256, False, 644)])
+def test_interaction_node_update_kernel_vs_fp64(h, last, tile, syn4):
+    """k_node_update / k_node_pair alone (the fused CFConv aggregation + transposed tcgen05 node linears) against an fp64
+    torch evaluation of the same operator on a replicated golden graph (N = 1024 atoms, ragged last tile): h_out and
+    x1_next within the single-GEMM tf32 bound (1.5e-3 L2-relative); the aggregation inside is exact in fp32 before
+    rounding.  tile: the kernel shape (0 = the library's choice; 323 = two CTAs per 32 atoms, each owning 128 of the 256
+    output features, activations exchanged through distributed shared memory; H = 128 falls back to one CTA)."""
     from tsdiff_b200 import engine as E
     reps = 16
     n1 = syn4["atom_type"].numel()
@@ -224,10 +227,14 @@ def test_interaction_node_update_kernel_vs_fp64(h, last, syn4):
     blk = L.Interaction()
     blk.lin2, blk.lin = L.linear(w2, b2), L.linear(wl, bl)
     nxt = L.linear(w1, None)
-    L.check(lib.tsd_interaction_node_update(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), C.byref(blk),
-                                            None if last else C.byref(nxt), L.ptr(x1), L.ptr(filt), L.ptr(h_in), L.ptr(h_out),
-                                            None if last else L.ptr(x1_next), s), "tsd_interaction_node_update")
-    torch.cuda.synchronize()
+    lib.tsd_tune_node_tile(tile)
+    try:
+        L.check(lib.tsd_interaction_node_update(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), C.byref(blk),
+                                                None if last else C.byref(nxt), L.ptr(x1), L.ptr(filt), L.ptr(h_in),
+                                                L.ptr(h_out), None if last else L.ptr(x1_next), s), "tsd_interaction_node_update")
+        torch.cuda.synchronize()
+    finally:
+        lib.tsd_tune_node_tile(0)
     row, col = plan.row[:e].long(), plan.col[:e].long()
     pair = plan.edge_upair[:e].long()
     agg = torch.zeros(n, h, dtype=torch.float64, device=DEV).index_add_(0, col, x1.double()[row] * filt.double()[pair])

@@ -424,6 +424,279 @@ int node_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
   return TSD_OK;
 }
 
+__device__ __forceinline__ void nu_st_cluster1(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// ---- the pair variant (H = 256): BOTH CTAs of a cluster run the chained GEMMs, each on 128 of the 256 output features.
+// The single-leader kernel above streams every 256 KiB weight matrix through one SM's L2 port (127 GB/s: 2.1 us per
+// stage, three stages per block, on the critical path of the step).  Here a CTA streams only ITS half of every W
+// (128 rows: 1 us per stage), aggregates half of the tile's atoms, and after every stage stores its 128 features of the
+// NT atoms TF32-rounded into BOTH CTAs' B-operand buffers through distributed shared memory (16 KiB per stage).
+//   * the B operand ping-pongs between two buffers by stage parity: a CTA's epilogue of stage s writes the peer's input
+//     of stage s + 1 while the peer's MMAs may still be reading its input of stage s;
+//   * one M half per CTA means consecutive MMAs would hit the same accumulator and serialise (94 instead of 47 clk each,
+//     profiles/r2_umma_small_n.txt): the K steps alternate between two accumulators, summed in the epilogue;
+//   * the in-CSR ids of the CTA's atoms are staged BEFORE griddepcontrol.wait: they are written by the edge build at the
+//     start of the step, only x1 comes from the preceding node kernel.  (Also staging the x1 rows of the tile's reactions
+//     -- a contiguous range -- in shared memory with one bulk copy and gathering only the filter rows measured SLOWER,
+//     289 vs 279 us per step: the phase is bound by dependent latencies, not bytes; profiles/r3_node_pair_timeline.txt);
+//   * no CTA touches the peer's shared memory after the peer's last wait (its bar_x of the final stage), so no
+//     cluster barrier is needed before exit.
+template <int NT>
+__global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, const __grid_constant__ NodeMaps maps,
+                                                             int tmem_cols) {
+  constexpr int H = 256;
+  constexpr int NUM_KB = H / TC_BK;            // K panels per stage
+  constexpr int W_PANEL = 128 * TC_BK * 4;     // this CTA's 128 rows of one K panel
+  constexpr int KP = 4;                        // K panels per ring slot (one tcgen05.commit per 16 MMAs)
+  constexpr int W_SLOT = KP * W_PANEL;         // 64 KiB
+  constexpr int NUM_KS = NUM_KB / KP;          // slots per stage
+  constexpr int NSLOT = 2;                     // = one stage's half matrix in flight
+  constexpr int X_PANEL = NT * TC_BK * 4;
+  constexpr int X_BYTES = NUM_KB * X_PANEL;    // one B operand: NT x H floats
+  constexpr int NA = NT / 2;                   // atoms aggregated by one CTA
+  constexpr int NW = NU_WORKERS * 32;
+  constexpr int CW = NT / 4;                   // accumulator columns (atoms) per epilogue warp
+  static_assert(CW == 8, "NT must be 32 (two NT x 256 B operands + the weight ring fill the shared memory)");
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ uint64_t bar_full[NSLOT];
+  __shared__ uint64_t bar_empty[NSLOT];
+  __shared__ uint64_t bar_x[3];    // B operand of stage s complete: every worker thread of BOTH CTAs arrives
+  __shared__ uint64_t bar_acc[2];  // accumulator set b complete (tcgen05.commit)
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_ptr[NA + 1];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) NU_STAMP(0);
+  const uint32_t rank = nu_cluster_rank();
+  const int npc = p.nodes_per_cluster > 0 ? min(p.nodes_per_cluster, NT) : NT;
+  const int node0 = (blockIdx.x / 2) * npc;       // first atom of the cluster's tile
+  const int N = min(p.num_nodes, node0 + npc);    // atoms past the tile belong to the next cluster
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  // layout: B operand 0 | staged in-CSR ids | ring slot 0 | ring slot 1 | B operand 1
+  uint8_t* stage_area = smem_gen + X_BYTES;
+  uint8_t* ring = stage_area + NU_STAGE_BYTES;
+  const uint32_t ring_base = smem_base + X_BYTES + NU_STAGE_BYTES;
+  const uint32_t xbuf0 = smem_base, xbuf1 = ring_base + 2 * W_SLOT;  // (an indexed array would live in local memory)
+  const int total_slots = p.num_stages * NUM_KS;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < 3; ++s) mbar_init(&bar_x[s], 2 * NW);
+    mbar_init(&bar_acc[0], 1);
+    mbar_init(&bar_acc[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == NU_WORKERS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // the peer's barriers exist before this CTA arrives on them
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) NU_STAMP(1);
+
+  if (warp == NU_WORKERS) {
+    // ------------------------------------------------------------------ TMA producer: this CTA's half of every W
+    if (lane == 0) {
+      for (int s = 0; s < p.num_stages; ++s)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[s])) : "memory");
+      for (int g = 0; g < total_slots; ++g) {
+        const int slot = g % NSLOT, round = g / NSLOT;
+        if (round > 0) mbar_wait(&bar_empty[slot], (uint32_t)((round - 1) & 1));
+        mbar_arrive_expect_tx(&bar_full[slot], (uint32_t)W_SLOT);
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          tma_load_2d(ring + (size_t)slot * W_SLOT + (size_t)k * W_PANEL, &maps.w[g / NUM_KS], &bar_full[slot],
+                      ((g % NUM_KS) * KP + k) * TC_BK, (int)rank * 128);
+      }
+    }
+  } else if (warp == NU_WORKERS + 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(NT);
+      for (int s = 0; s < p.num_stages; ++s) {
+        const int b = s & 1;
+        nu_wait_cluster(&bar_x[s], 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (remote) generic-proxy writes -> UMMA reads
+        tc_fence_after();
+        NU_STAMP(8 + 4 * s);
+        const uint32_t xaddr = b ? xbuf1 : xbuf0;
+        for (int ks = 0; ks < NUM_KS; ++ks) {
+          const int g = s * NUM_KS + ks;
+          const int slot = g % NSLOT, round = g / NSLOT;
+          mbar_wait(&bar_full[slot], (uint32_t)(round & 1));
+          tc_fence_after();
+          if (ks == 0) NU_STAMP(9 + 4 * s);
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            const int kb = ks * KP + k;
+            const uint64_t bdesc = umma_desc_sw128(xaddr + (uint32_t)(kb * X_PANEL));
+            const uint64_t adesc = umma_desc_sw128(ring_base + (uint32_t)(slot * W_SLOT + k * W_PANEL));
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 8; ++kk)
+              umma_tf32(tmem + (uint32_t)((b * 2 + (kk & 1)) * NT), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk),
+                        idesc, (kb != 0 || kk >= 2) ? 1u : 0u);
+          }
+          umma_commit(&bar_empty[slot]);
+        }
+        umma_commit(&bar_acc[b]);
+        NU_STAMP(10 + 4 * s);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ workers
+    const uint32_t peer = rank ^ 1u;
+    // (1) this CTA's NA atoms of the stage-0 B operand -> both CTAs' buffer 0
+    {
+      constexpr int CAP = NU_STAGE_BYTES / 8;
+      int* s_eid = reinterpret_cast<int*>(stage_area);
+      int* s_src = s_eid + CAP;
+      const int my0 = (int)rank * NA;
+      // the in-CSR ids: written by the edge build at the start of the step (complete before the first node kernel
+      // started), not by the preceding node kernel -- no need to wait for it
+      for (int i = tid; i <= NA; i += NW) s_ptr[i] = p.in_ptr[min(node0 + my0 + i, N)];
+      asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
+      const int seg0 = s_ptr[0], seg_n = s_ptr[NA] - seg0;
+      const bool staged = seg_n <= CAP;
+      if (staged) {
+        for (int i = tid; i < seg_n; i += NW) {
+          s_eid[i] = p.in_eid[seg0 + i];
+          s_src[i] = p.in_src[seg0 + i];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
+      }
+      const int* eids = staged ? s_eid - seg0 : p.in_eid;
+      const int* srcs = staged ? s_src - seg0 : p.in_src;
+      const uint32_t x_own = nu_mapa(smem_base, rank), x_peer = nu_mapa(smem_base, peer);
+      pdl_wait();  // see k_node_update
+      pdl_trigger();
+      if (tid == 0) NU_STAMP(7);
+      for (int item = warp; item < NA * 2; item += NU_WORKERS) {
+        const int n = item >> 1, slab = item & 1;
+        const int off = slab * 128 + lane * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the tile: zeros (their output columns are never stored)
+        if (node0 + my0 + n < N) acc = nu_aggregate_item(p, eids, srcs, s_ptr[n], s_ptr[n + 1], off, lane);
+        const float4 r = tf32_rn4(acc);
+        const uint32_t o = (uint32_t)((off >> 5) * X_PANEL) + sw128_off(my0 + n, (off & 31) >> 2);
+        nu_st_cluster4(x_own + o, r);
+        nu_st_cluster4(x_peer + o, r);
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> async proxy (both CTAs' UMMA)
+      nu_arrive_cluster(nu_mapa(smem_u32(&bar_x[0]), rank));
+      nu_arrive_cluster(nu_mapa(smem_u32(&bar_x[0]), peer));
+      if (tid == 0) NU_STAMP(2);
+    }
+    // (2) epilogues.  warp -> TMEM lane quarter q (hardware: warp_id % 4) = 32 of this CTA's 128 features, atom group cs
+    const int q = warp & 3, cs = warp >> 2;
+    const int f = (int)rank * 128 + q * 32 + lane;
+    const int n0 = cs * CW;
+    for (int s = 0; s < p.num_stages; ++s) {
+      const int b = s & 1;
+      const float* const st_bias = p.st[s].bias;  // in registers: see k_node_update
+      const float* const st_res = p.st[s].residual;
+      float* const st_store = p.st[s].store;
+      const bool st_ssp = p.st[s].act == TSD_ACT_SSP;
+      const bool feeds = s + 1 < p.num_stages;
+      const float bias = st_bias ? __ldg(st_bias + f) : 0.f;
+      float res[CW];
+      if (st_res) {  // independent of the accumulator: in flight behind the MMA
+#pragma unroll
+        for (int j = 0; j < CW; ++j) res[j] = st_res[(size_t)min(node0 + n0 + j, N - 1) * H + f];
+      }
+      mbar_wait(&bar_acc[b], (uint32_t)((s >> 1) & 1));
+      tc_fence_after();
+      if (tid == 0) NU_STAMP(11 + 4 * s);
+      uint32_t v0[CW], v1[CW];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 2 * NT + n0);
+      tmem_ld_cols_async<CW>(taddr, v0);
+      tmem_ld_cols_async<CW>(taddr + (uint32_t)NT, v1);
+      tmem_wait_ld();
+      const uint32_t xo = (((s + 1) & 1) ? xbuf1 : xbuf0) + (uint32_t)((f >> 5) * X_PANEL + ((f & 3) << 2));
+      const uint32_t x_own = nu_mapa(xo, rank), x_peer = nu_mapa(xo, peer);
+      const int chunk = (f & 31) >> 2;
+      float r[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        r[j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) + bias;
+        if (st_ssp) r[j] = tc_act<TSD_ACT_SSP>(r[j]);
+        if (st_res) r[j] += res[j];
+      }
+      // the next stage's operand first: the release of the arrivals below would otherwise wait for the acknowledgement of
+      // the global stores as well (1.1 us per stage measured, profiles/r3_node_pair_timeline.txt)
+      if (feeds) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const int n = n0 + j;
+          const uint32_t o = (uint32_t)(n * 128 + ((chunk ^ (n & 7)) << 4));
+          const float t = tf32_rn(r[j]);
+          nu_st_cluster1(x_own + o, t);
+          nu_st_cluster1(x_peer + o, t);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        tc_fence_before();
+        nu_arrive_cluster(nu_mapa(smem_u32(&bar_x[s + 1]), rank));
+        nu_arrive_cluster(nu_mapa(smem_u32(&bar_x[s + 1]), peer));
+      }
+      if (st_store) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+          if (node0 + n0 + j < N) st_store[(size_t)(node0 + n0 + j) * H + f] = r[j];
+      }
+      if (tid == 0) NU_STAMP(3 + s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) NU_STAMP(6);
+  if (warp == NU_WORKERS + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tmem_cols)
+                 : "memory");
+  }
+}
+
+template <int NT>
+int node_pair_launch(const NodeArgs& a, const NodeMaps& maps, cudaStream_t stream) {
+  constexpr int X_BYTES = NT * 256 * 4, W_SLOT = 4 * 128 * TC_BK * 4;
+  const size_t smem = 1024 + (size_t)2 * X_BYTES + NU_STAGE_BYTES + (size_t)2 * W_SLOT;
+  static size_t attr_smem = 0;  // per instantiation
+  if (smem > attr_smem) {
+    TSD_CUDA(cudaFuncSetAttribute(k_node_pair<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  int tmem_cols = 32;  // a power of two >= 32 that holds 2 accumulator sets x 2 K parities x NT columns
+  while (tmem_cols < 4 * NT) tmem_cols *= 2;
+  cudaLaunchConfig_t cfg = {};
+  const int npc = a.nodes_per_cluster > 0 && a.nodes_per_cluster < NT ? a.nodes_per_cluster : NT;
+  cfg.gridDim = dim3(tsd_ceil_div(a.num_nodes, npc) * 2);
+  cfg.blockDim = dim3(NU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_node_pdl ? 2 : 1;
+  TSD_CUDA(cudaLaunchKernelEx(&cfg, k_node_pair<NT>, a, maps, tmem_cols));
+  TSD_LAUNCH_CHECK();
+  return TSD_OK;
+}
+
 }  // namespace
 
 // Rows per CTA: enough CTAs to spread the aggregation's gathers over the GPU, few enough that the weight
@@ -442,12 +715,13 @@ extern "C" void tsd_tune_node_tile(int code) { g_node_tile_override = code; }
 // Measured at batch 100 (profiles/r2_variants_*.txt, profiles/r3_stack_modes.txt): fewer atoms per CTA shorten the
 // aggregation phase (bound by one SM's L2 ingest, 127 GB/s) but multiply the weight streams and the CTAs that compete
 // with concurrently running filter kernels for SMs; more atoms per CTA (48, 64) lengthen the serial node chain.  Next to
-// per-block filter kernels one CTA per 32 atoms is best; when the node chain runs alone (behind the filter stack) a
-// cluster of two CTAs that share the gathers of a 32-atom tile is (the second CTA exits after its half).
+// per-block filter kernels one CTA per 32 atoms is best; when the node chain runs alone (behind the filter stack) the
+// pair kernel is (two CTAs share a 32-atom tile's gathers AND split the output features of the GEMMs; H = 128 and
+// dense inputs fall back to 322 / 321).
 int tsd_node_tile(bool alone, int* nodes_per_cluster) {
   *nodes_per_cluster = 0;
   if (g_node_tile_override > 0) return g_node_tile_override;
-  return alone ? 322 : 321;
+  return alone ? 323 : 321;
 }
 
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
@@ -455,13 +729,17 @@ int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {
   if (!(a.H == 128 || a.H == 256) || a.num_stages < 1 || a.num_stages > 3) return TSD_ERR_UNSUPPORTED;
   if (a.num_nodes <= 0) return TSD_OK;
   TSD_REQUIRE(a.x || (a.in_ptr && a.in_eid && a.in_src && a.x1 && a.filt));
+  // the pair variant (code NT * 10 + 3) needs the fused aggregation and H = 256; other inputs take the one-CTA shape
+  if (tile % 10 == 3 && (a.x || a.H != 256)) tile = a.x ? 321 : 322;
   NodeMaps maps;
   for (int s = 0; s < 3; ++s) {
     const float* w = a.st[s < a.num_stages ? s : 0].W;
     TSD_REQUIRE(w);
     if (reinterpret_cast<uintptr_t>(w) & 15) return TSD_ERR_UNSUPPORTED;
-    if (!make_tensor_map(&maps.w[s], w, (uint64_t)a.H, (uint64_t)a.H, (uint32_t)a.H)) return TSD_ERR_UNSUPPORTED;
+    if (!make_tensor_map(&maps.w[s], w, (uint64_t)a.H, (uint64_t)a.H, tile % 10 == 3 ? 128u : (uint32_t)a.H))
+      return TSD_ERR_UNSUPPORTED;
   }
+  if (tile == 323) return node_pair_launch<32>(a, maps, stream);
 #define NU_GO(NT, C)                                                  \
   if (tile == NT * 10 + C)                                            \
     return a.H == 256 ? node_launch<256, NT, C>(a, maps, stream) : node_launch<128, NT, C>(a, maps, stream)
