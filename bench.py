@@ -279,7 +279,7 @@ def api_call(args, models, data_host, device, group=None):
 def committed_traffic():
     """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the top kernels, from
     the committed `ncu --set full` captures (profiles/r2_ncu_traffic.json, else round 1's)."""
-    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+    for name in ("r3_ncu_traffic.json", "r2_ncu_traffic.json", "r1_ncu_traffic.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             return json.load(open(path))
@@ -334,18 +334,29 @@ def kernel_rooflines(args, eng, peaks, device):
     blocks = eng.members[0]["blocks"] if hasattr(eng, "members") else eng.blocks
     math = L.MATH[args.math]
     traffic = committed_traffic()
-    t_f = timed_cold(lambda: L.check(lib.tsd_filter_network(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), L.ptr(x),
-                                                            C.byref(blocks[0]), L.ptr(tmp), L.ptr(out), math, stream),
-                                     "tsd_filter_network"), flush)
-    # executed = what the kernel computes: two rows x H x H layers, one row per unordered pair (both directions of an
-    # edge are bit-identical); reference-equivalent = the same over the DIRECTED edges
-    executed = 2 * 2.0 * e * h * h
-    equivalent = 2 * 2.0 * e_dir * h * h
     tf32 = args.math == "tf32"
+    n_blk = len(blocks)
+    stacked = tf32 and h in (128, 256) and plan.work_capacity >= 1024 and n_blk <= 8
+    if stacked:
+        # tf32: the filter networks of ALL interaction blocks are one launch (k_filter_stack), as inside the step
+        fbufs = torch.empty(n_blk, max(plan.work_capacity, 1), h, dtype=torch.float32, device=device)
+        fptrs = (C.c_void_p * n_blk)(*[fbufs[i].data_ptr() for i in range(n_blk)])
+        t_f = timed_cold(lambda: L.check(lib.tsd_filter_stack(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), L.ptr(x),
+                                                              blocks, n_blk, fptrs, stream), "tsd_filter_stack"), flush)
+        layers = n_blk
+    else:
+        t_f = timed_cold(lambda: L.check(lib.tsd_filter_network(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges),
+                                                                L.ptr(x), C.byref(blocks[0]), L.ptr(tmp), L.ptr(out), math,
+                                                                stream), "tsd_filter_network"), flush)
+        layers = 1
+    # executed = what the kernel computes: two rows x H x H layers per block, one row per unordered pair (both directions
+    # of an edge are bit-identical); reference-equivalent = the same over the DIRECTED edges
+    executed = layers * 2 * 2.0 * e * h * h
+    equivalent = layers * 2 * 2.0 * e_dir * h * h
     peak = peaks["tensor_burst"] / 2 if tf32 else 75.0
-    kname = "k_chain_tf32" if tf32 else "k_gemm_ffma"
-    tensor = {"bound": "tensor", "kernel": "%s: CFConv filter network nn2(ssp(nn0(edge_attr)))*C, 2 x (rows x %d x %d), %s"
-                                           % (kname, h, h, args.math),
+    kname = "k_filter_stack" if stacked else ("k_chain_tf32" if tf32 else "k_gemm_ffma")
+    tensor = {"bound": "tensor", "kernel": "%s: CFConv filter networks nn2(ssp(nn0(edge_attr)))*C of %d block(s), %d x 2 x "
+                                           "(rows x %d x %d), %s" % (kname, layers, layers, h, h, args.math),
               "achieved": executed / t_f / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": executed / t_f / 1e12 / peak,
               "traffic": traffic.get(kname),
               "peak_source": (peaks["source"] + " bf16 burst / 2 = TF32 dense peak (kind::tf32 runs at half the bf16 rate)")
@@ -353,7 +364,8 @@ def kernel_rooflines(args, eng, peaks, device):
               "definition": "achieved = EXECUTED flops / time (one row per unordered pair)",
               "us_per_launch": t_f * 1e6, "rows": e, "executed_flops": executed,
               "reference_equivalent_flops": equivalent, "reference_equivalent_tflops": equivalent / t_f / 1e12,
-              "algorithmic_bytes": 2 * e * h * 4 + 2 * h * h * 4}
+              "blocks_per_launch": layers,
+              "algorithmic_bytes": (1 + layers) * e * h * 4 + layers * 2 * h * h * 4}
     x1 = ws.node[1]
     agg = ws.node[2]
     t_agg = timed_cold(lambda: L.check(lib.tsd_cfconv_aggregate(C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), h,
@@ -378,9 +390,12 @@ def kernel_rooflines(args, eng, peaks, device):
             C.byref(plan.c_work_batch), C.byref(plan.c_work_edges), C.byref(blocks[0]), C.byref(nxt), L.ptr(x1), L.ptr(out),
             L.ptr(hb), L.ptr(hout), L.ptr(x1n), stream), "tsd_interaction_node_update"), flush)
         nb = nbytes + 3 * n * h * 4 + 3 * h * h * 4  # + h in, h out, x1_next, three weight matrices
-        node = {"bound": "hbm", "kernel": "k_node_update: CFConv aggregation fused into the node linears (swap-AB tcgen05, "
-                                          "32 atoms per CTA)", "achieved": nb / t_n / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": nb / t_n / 1e9 / peaks["hbm"], "traffic": traffic.get("k_node_update"), "us_per_launch": t_n * 1e6,
+        node = {"bound": "hbm", "kernel": "k_node_pair: CFConv aggregation fused into the node linears (swap-AB tcgen05, two "
+                                          "CTAs per 32 atoms, each 128 of the 256 output features)" if h == 256 else
+                                          "k_node_update: CFConv aggregation fused into the node linears (swap-AB tcgen05)",
+                "achieved": nb / t_n / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": nb / t_n / 1e9 / peaks["hbm"],
+                "traffic": traffic.get("k_node_pair" if h == 256 else "k_node_update"), "us_per_launch": t_n * 1e6,
                 "algorithmic_bytes": nb, "executed_flops": 3 * 2.0 * n * h * h,
                 "regime": "latency / per-SM ingest bound: every CTA gathers its atoms' filter rows through one SM's L2 port "
                           "(127 GB/s measured, profiles/r2_tma_stream.txt) and streams the three weight matrices"}

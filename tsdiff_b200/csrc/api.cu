@@ -385,7 +385,7 @@ extern "C" int tsd_interaction_node_update(const tsd_batch_t* batch, const tsd_e
   NodeArgs na;
   memset(&na, 0, sizeof(na));
   int npc = 0;
-  const int tile = tsd_node_tile(true, &npc);  // a single launch has the GPU to itself
+  const int tile = tsd_node_tile(true, batch->num_nodes, &npc);  // a single launch has the GPU to itself
   na.num_nodes = batch->num_nodes;
   na.nodes_per_cluster = npc;
   na.H = H;
@@ -527,6 +527,9 @@ extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edg
 // tuning hook of profiles/scripts (not part of the C-ABI header): -1 = one filter kernel per block (round-2 path),
 // 0 = all blocks in one launch, k > 0 = two launches, blocks [0, k) and [k, L)
 static int g_filter_stack_mode = 0;
+// programmatic dependent launch of the edge-side GEMM kernels (gemm_tc.cu, gemm_chain.cu)
+int g_tsd_gemm_pdl = 1;
+extern "C" void tsd_tune_gemm_pdl(int on) { g_tsd_gemm_pdl = on; }
 extern "C" void tsd_tune_filter_stack(int code) { g_filter_stack_mode = code; }
 
 // Whole SchNet encoder (schnet.py:203-225).  fp32 mode: one tsd_cfconv_layer per block.  tf32
@@ -624,8 +627,9 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     }
     // Node kernel shape: behind the filter stack the node chain has the GPU to itself, so two CTAs share a 32-atom tile's
     // gathers; next to per-block filter kernels one CTA per tile competes least for SMs (profiles/r3_stack_modes.txt).
-    const int tile = tsd_node_tile(stacked && stack_cut == num_blocks, &npc);
-    TSD_TRY(tsd_node_update_tf32(na, tsd_node_tile(false, &npc), side));  // x1 of block 0: a dense input, no gathers
+    int npc0 = 0;
+    TSD_TRY(tsd_node_update_tf32(na, tsd_node_tile(false, batch->num_nodes, &npc0), side));  // x1 of block 0: dense input
+    const int tile = tsd_node_tile(stacked && stack_cut == num_blocks, batch->num_nodes, &npc);
     for (int l = 0; l < num_blocks; ++l) {
       const tsd_interaction_t& b = blocks[l];
       float* filt = fbuf[l % nbuf];

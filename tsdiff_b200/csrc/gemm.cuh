@@ -188,7 +188,7 @@ struct FilterStackArgs {
 };
 int tsd_filter_stack_tf32(const FilterStackArgs& a, cudaStream_t stream);
 
-int tsd_node_tile(bool alone, int* nodes_per_cluster);  // node_update.cu: kernel shape
+int tsd_node_tile(bool alone, int num_nodes, int* nodes_per_cluster);  // node_update.cu: kernel shape
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream);
 int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream);           // gemm_chain.cu
 int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream);        // dispatch (api.cu)

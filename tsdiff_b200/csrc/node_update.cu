@@ -563,12 +563,14 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       constexpr int CAP = NU_STAGE_BYTES / 8;
       int* s_eid = reinterpret_cast<int*>(stage_area);
       int* s_src = s_eid + CAP;
-      const int my0 = (int)rank * NA;
+      // the cluster's npc atoms are split evenly between the two CTAs (npc < NT when the host sizes the tiles to the SMs)
+      const int na0 = (npc + 1) >> 1;
+      const int my0 = rank == 0 ? 0 : na0, my_n = rank == 0 ? na0 : npc - na0;
       // the in-CSR ids: written by the edge build at the start of the step (complete before the first node kernel
       // started), not by the preceding node kernel -- no need to wait for it
-      for (int i = tid; i <= NA; i += NW) s_ptr[i] = p.in_ptr[min(node0 + my0 + i, N)];
+      for (int i = tid; i <= my_n; i += NW) s_ptr[i] = p.in_ptr[min(node0 + my0 + i, N)];
       asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
-      const int seg0 = s_ptr[0], seg_n = s_ptr[NA] - seg0;
+      const int seg0 = s_ptr[0], seg_n = s_ptr[my_n] - seg0;
       const bool staged = seg_n <= CAP;
       if (staged) {
         for (int i = tid; i < seg_n; i += NW) {
@@ -583,7 +585,9 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       pdl_wait();  // see k_node_update
       pdl_trigger();
       if (tid == 0) NU_STAMP(7);
-      for (int item = warp; item < NA * 2; item += NU_WORKERS) {
+      // rows [npc, NT) of the B operand (padding of the MMA shape) are never written: their accumulator columns are
+      // garbage that no epilogue stores
+      for (int item = warp; item < my_n * 2; item += NU_WORKERS) {
         const int n = item >> 1, slab = item & 1;
         const int off = slab * 128 + lane * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the tile: zeros (their output columns are never stored)
@@ -706,7 +710,8 @@ extern "C" void tsd_node_dbg_read(unsigned long long* out) { cudaMemcpyFromSymbo
 extern "C" void tsd_node_cta_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_node_cta, sizeof(g_node_cta)); }
 #endif
 extern "C" void tsd_tune_node_pdl(int on) { g_node_pdl = on; }
-static int g_node_tile_override = 0;
+static int g_node_tile_override = 0, g_node_npc_override = 0;
+extern "C" void tsd_tune_node_npc(int atoms) { g_node_npc_override = atoms; }
 // tuning hook of profiles/scripts (not part of the C-ABI header): code = atoms per cluster * 10 + CTAs per cluster,
 // 0 restores the built-in choice
 extern "C" void tsd_tune_node_tile(int code) { g_node_tile_override = code; }
@@ -718,10 +723,27 @@ extern "C" void tsd_tune_node_tile(int code) { g_node_tile_override = code; }
 // per-block filter kernels one CTA per 32 atoms is best; when the node chain runs alone (behind the filter stack) the
 // pair kernel is (two CTAs share a 32-atom tile's gathers AND split the output features of the GEMMs; H = 128 and
 // dense inputs fall back to 322 / 321).
-int tsd_node_tile(bool alone, int* nodes_per_cluster) {
-  *nodes_per_cluster = 0;
+// The pair kernel's clusters take fewer than 32 atoms when that spreads the gathers over more SMs: as many clusters as
+// fit 90 % of the SMs at one CTA each (the rest is where the next node kernel's CTAs set up under programmatic dependent
+// launch); measured at batch 100 (1826 atoms): 28 atoms per cluster 273 us per step, 32: 277, 26: 280, 25 (all SMs): 291.
+int tsd_node_tile(bool alone, int num_nodes, int* nodes_per_cluster) {
+  *nodes_per_cluster = g_node_npc_override;
   if (g_node_tile_override > 0) return g_node_tile_override;
-  return alone ? 323 : 321;
+  if (!alone) return 321;
+  if (g_node_npc_override == 0) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess ||
+          cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        num_sms = 148;
+    }
+    const int clusters = num_sms * 9 / 20;
+    int npc = clusters > 0 ? tsd_ceil_div(num_nodes, clusters) : 32;
+    npc = npc < 8 ? 8 : npc;
+    *nodes_per_cluster = npc >= 32 ? 0 : npc;
+  }
+  return 323;
 }
 
 int tsd_node_update_tf32(const NodeArgs& a, int tile, cudaStream_t stream) {

@@ -7,6 +7,8 @@
 
 #include "gemm.cuh"
 
+extern int g_tsd_gemm_pdl;  // api.cu
+
 namespace tc {
 
 constexpr int TC_BM = 128;
@@ -289,9 +291,8 @@ static inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// measured neutral on the Langevin step (the step is bound by SM residency, not by launch gaps):
-// the attribute stays off, the kernels keep their griddepcontrol instructions (no-ops without it)
-static inline bool pdl_enabled() { return false; }
+// run-time switch (api.cu; tuning hook tsd_tune_gemm_pdl): without the attribute the griddepcontrol instructions are no-ops
+static inline bool pdl_enabled() { return g_tsd_gemm_pdl != 0; }
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
