@@ -1,6 +1,6 @@
 """Langevin-step time (CUDA-graph replays, late-trajectory edge count) for the filter-stack launch modes and node tiles
 in ONE process: the tuning hooks are run-time switches, every mode re-captures its graph.
-usage: python profiles/scripts/stack_modes.py [mode:tile[:pdl[:stack_ctas[:gemm_pdl[:atoms_per_node_cluster]]]] ...]   (mode -1 = one filter kernel per block)"""
+usage: python profiles/scripts/stack_modes.py [mode:tile[:pdl[:stack_ctas[:gemm_pdl[:atoms_per_node_cluster[:chain2]]]]] ...]   (mode -1 = one filter kernel per block)"""
 import sys, json, torch
 sys.path.insert(0, '.')
 import bench
@@ -21,10 +21,12 @@ for spec in specs:
     lib.tsd_tune_node_pdl(pdl)
     grid = f[3] if len(f) > 3 else 0
     lib.tsd_tune_filter_stack_grid(grid)
-    gpdl = f[4] if len(f) > 4 else 0
+    gpdl = f[4] if len(f) > 4 else 1
     lib.tsd_tune_gemm_pdl(gpdl)
     npc = f[5] if len(f) > 5 else 0
     lib.tsd_tune_node_npc(npc)
+    chain2 = f[6] if len(f) > 6 else 1
+    lib.tsd_tune_gemm_chain2(chain2)
     lib.tsd_tune_filter_stack(mode)
     lib.tsd_tune_node_tile(tile)
     torch.manual_seed(0)
@@ -35,7 +37,7 @@ for spec in specs:
     t0.record()
     for _ in range(1500): runner.graph.replay()
     t1.record(); torch.cuda.synchronize()
-    out = {"mode": mode, "tile": tile, "pdl": pdl, "stack_ctas": grid, "gemm_pdl": gpdl, "npc": npc, "step_us": t0.elapsed_time(t1) / 1500 * 1e3,
+    out = {"mode": mode, "tile": tile, "pdl": pdl, "stack_ctas": grid, "gemm_pdl": gpdl, "npc": npc, "chain2": chain2, "step_us": t0.elapsed_time(t1) / 1500 * 1e3,
            "pairs": eng.plan.work_count()}
     if pos is not None:
         if ref_pos is None: ref_pos = pos

@@ -74,12 +74,27 @@ extern "C" const char* tsd_error_string(int code) {
   }
 }
 
+int g_tsd_gemm_chain2 = 1;
+extern "C" void tsd_tune_gemm_chain2(int on) { g_tsd_gemm_chain2 = on; }
+
 int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream) {
   if (math == TSD_MATH_TF32) {
     int rc = tsd_gemm_tf32(g, stream);
     if (rc != TSD_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core kernel does not take run on FFMA
   }
   return tsd_gemm_ffma(g, stream);
+}
+
+// tf32: layer `g` and the layer `next` chained on the tile (gemm_tc.cu; the intermediate never leaves tensor memory).
+// `g` describes the first layer with the SECOND layer's output fields (C / ldc / round_out or w3 / b3 / out_vec).
+// Returns TSD_ERR_UNSUPPORTED when the caller has to run the two layers as separate kernels.
+static int tsd_gemm_chain2(GemmArgs g, const tsd_linear_t& next, int math, cudaStream_t stream) {
+  if (math != TSD_MATH_TF32 || !g_tsd_gemm_chain2 || next.in_features != g.N) return TSD_ERR_UNSUPPORTED;
+  g.W2 = next.weight;
+  g.bias2 = next.bias;
+  g.N2 = next.out_features;
+  g.ldc = g.N2;
+  return tsd_gemm_chain2_tf32(g, stream);
 }
 
 #define TSD_TRY(expr)        \
@@ -152,13 +167,16 @@ extern "C" int tsd_edge_embed(const tsd_batch_t* batch, const tsd_edges_t* edges
     g.emb = enc->bond_emb;
     g.code = code;
     g.act = enc->cat_act;
+    g.round_out = 1;  // feeds cat2 / edge_attr feeds the filter networks and the pair MLP
+    g.C = out;
+    int rc = tsd_gemm_chain2(g, *enc->cat2, math, s);  // cat0 -> cat2 on the tile
+    if (rc != TSD_ERR_UNSUPPORTED) return rc;
     g.C = tmp;
-    g.round_out = 1;  // feeds cat2
     TSD_TRY(tsd_gemm(g, math, s));
     GemmArgs g2 = edge_gemm(batch, edges, *enc->cat2);
     g2.A = tmp;
     g2.C = out;
-    g2.round_out = 1;  // edge_attr feeds the filter networks and the pair MLP
+    g2.round_out = 1;
     TSD_TRY(tsd_gemm(g2, math, s));
   }
   return TSD_OK;
@@ -229,8 +247,11 @@ extern "C" int tsd_edge_embed_delta(const tsd_batch_t* batch, const tsd_edges_t*
   g.code = code1;
   g.row_index = diff_rows;
   g.act = enc->cat_act;
-  g.C = tmp;
   g.round_out = 1;
+  g.C = out_compact;
+  int rc = tsd_gemm_chain2(g, *enc->cat2, math, s);
+  if (rc != TSD_ERR_UNSUPPORTED) return rc;
+  g.C = tmp;
   TSD_TRY(tsd_gemm(g, math, s));
   GemmArgs g2 = edge_gemm(batch, edges, *enc->cat2);
   g2.M_ptr = diff_count;
@@ -330,6 +351,15 @@ extern "C" int tsd_pair_mlp_delta(const tsd_batch_t* batch, const tsd_edges_t* e
   g.alt_A = alt_attr;
   g.alt_pos = alt_pos;
   g.act = mlp->act;
+  {
+    GemmArgs c = g;  // l0 -> l1 -> row-dot with l2 on the tile
+    c.w3 = mlp->l2.weight;
+    c.b3 = mlp->l2.bias;
+    c.out_vec = edge_inv;
+    c.accumulate = accumulate;
+    int rc = tsd_gemm_chain2(c, mlp->l1, math, s);
+    if (rc != TSD_ERR_UNSUPPORTED) return rc;
+  }
   g.C = ef0;
   g.round_out = 1;  // feeds l1
   TSD_TRY(tsd_gemm(g, math, s));

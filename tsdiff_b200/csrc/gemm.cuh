@@ -55,6 +55,13 @@ struct GemmArgs {
   float* out_vec;
   int accumulate;
   int round_out;           // tf32 mode: round stored outputs to TF32 (RNE) because a tensor-core GEMM consumes them
+  // tf32 tensor-core kernel only (tsd_gemm_chain2_tf32): a SECOND linear layer chained on the same 128-row tile,
+  //   out = epilogue( act2( act(Aop W^T + bias) W2^T + bias2 ) ),   W2: (N2, N) row-major, act2 = act for the row-dot
+  // epilogue and none otherwise.  The first layer's output stays in tensor memory (the A operand of the second MMA);
+  // C / ldc / round_out / w3 / b3 / out_vec / accumulate describe the second layer's output.
+  const float* W2;
+  const float* bias2;
+  int N2;
 };
 
 static inline GemmArgs tsd_gemm_args() {
@@ -194,3 +201,4 @@ int tsd_chain_tf32(const ChainArgs& c, cudaStream_t stream);           // gemm_c
 int tsd_gemm(const GemmArgs& g, int math, cudaStream_t stream);        // dispatch (api.cu)
 int tsd_gemm_ffma(const GemmArgs& g, cudaStream_t stream);             // gemm_ffma.cu
 int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream);             // gemm_tc.cu
+int tsd_gemm_chain2_tf32(const GemmArgs& g, cudaStream_t stream);      // gemm_tc.cu: two chained layers (GemmArgs.W2)

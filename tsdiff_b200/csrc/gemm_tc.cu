@@ -102,15 +102,21 @@ __device__ __forceinline__ float4 tc_load_a4(const GemmArgs& p, int m, int k, in
   return *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + k);
 }
 
-template <int ACT, int EPI, int AKIND, int NT>
+// CHAIN: a second layer W2 (N2 x N) on the same tile.  After the first main loop every thread rewrites its part of the
+// accumulator IN PLACE as tf32(act(acc + bias)) (tcgen05.ld / tcgen05.st), which the second main loop reads as its A
+// operand straight from tensor memory; W2 streams through the same shared-memory ring (its first panels already while
+// the first layer's last MMAs drain); the second accumulator sits in the TMEM columns behind the first.
+template <int ACT, int EPI, int AKIND, int NT, bool CHAIN>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
     k_gemm_tf32(const GemmArgs p, int tmem_cols, const __grid_constant__ CUtensorMap map_a,
-                const __grid_constant__ CUtensorMap map_w) {
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w2) {
   extern __shared__ uint8_t smem_dyn[];
   constexpr int TC_STAGES = tc_stages(NT);
   __shared__ uint64_t bar_full[TC_STAGES];
   __shared__ uint64_t bar_empty[TC_STAGES];
   __shared__ uint64_t bar_accum;
+  __shared__ uint64_t bar_full2[TC_STAGES];  // CHAIN: W2 panels (TMA bytes only)
+  __shared__ uint64_t bar_accum2;
   __shared__ uint32_t tmem_base_s;
   constexpr int TC_GROUP_THREADS = tc_group_threads(NT);
   constexpr int NSL = NT / 128;  // column slices of the epilogue (warps per TMEM lane quarter)
@@ -125,6 +131,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_accum, 1);
+    if (CHAIN) {
+      for (int s = 0; s < TC_STAGES; ++s) mbar_init(&bar_full2[s], 1);
+      mbar_init(&bar_accum2, 1);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w2)) : "memory");
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     if (dense_a) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -151,6 +162,16 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const int num_kb = K / TC_BK;
+  // CHAIN: the second layer's K panels (K2 = N) continue the ring's panel count; W2 panel j goes to slot (num_kb + j) %
+  // stages once the MMAs that read the slot before have retired
+  const int num_kb2 = CHAIN ? N / TC_BK : 0;
+  const int N2 = CHAIN ? p.N2 : 0;
+  auto load_w2_panel = [&](int j) {
+    const int g = num_kb + j, s = g % TC_STAGES, round = g / TC_STAGES;
+    if (round > 0) mbar_wait(&bar_empty[s], (uint32_t)((round - 1) & 1));
+    mbar_arrive_expect_tx(&bar_full2[s], (uint32_t)N2 * TC_BK * 4);
+    tma_load_2d(smem_gen + (size_t)s * stage_bytes + TC_A_PANEL_BYTES, &map_w2, &bar_full2[s], j * TC_BK, 0);
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -164,6 +185,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
         if (dense_a) tma_load_2d(a_panel, &map_a, &bar_full[s], kb * TC_BK, m0);
         tma_load_2d(a_panel + TC_A_PANEL_BYTES, &map_w, &bar_full[s], kb * TC_BK, 0);
       }
+      // the first W2 panels only wait for MMAs of the FIRST layer: issued before this warp joins its epilogue
+      for (int j = 0; j < num_kb2 && j < TC_STAGES; ++j) load_w2_panel(j);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -228,26 +251,74 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
   const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter of this warp, column half
   const int row = q * 32 + lane, m = m0 + row;
   const bool live = m < M;
-  const int cols_per_half = N / NSL;
+  if (CHAIN) {
+    // ---- first layer's epilogue, in place: X = tf32(act(acc + bias)) becomes the A operand of the second layer
+    const int cols1 = N / NSL;
+    for (int cc = 0; cc < cols1; cc += 32) {
+      const int c0 = half * cols1 + cc;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      uint32_t v[32];
+      tmem_ld32(taddr, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j + 0] = __float_as_uint(tf32_rn(tc_act<ACT>(__uint_as_float(v[j + 0]) + b.x)));
+        v[j + 1] = __float_as_uint(tf32_rn(tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y)));
+        v[j + 2] = __float_as_uint(tf32_rn(tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z)));
+        v[j + 3] = __float_as_uint(tf32_rn(tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w)));
+      }
+      tmem_st32(taddr, v);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0 && lane == 0) {
+      for (int j = TC_STAGES; j < num_kb2; ++j) load_w2_panel(j);  // slots freed by the second layer's own MMAs
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc2 = umma_idesc_tf32(N2);
+      for (int j = 0; j < num_kb2; ++j) {
+        const int g = num_kb + j, s = g % TC_STAGES;
+        mbar_wait(&bar_full2[s], (uint32_t)((j / TC_STAGES) & 1));
+        tc_fence_after();
+        const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)s * stage_bytes + TC_A_PANEL_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk)
+          umma_tf32_ts(tmem + (uint32_t)N, tmem + (uint32_t)(j * TC_BK + kk * 8), bdesc + (uint64_t)(2 * kk), idesc2,
+                       (j | kk) != 0 ? 1u : 0u);
+        umma_commit(&bar_empty[s]);
+        if (j == num_kb2 - 1) umma_commit(&bar_accum2);
+      }
+    }
+    __syncwarp();
+    mbar_wait(&bar_accum2, 0);
+    tc_fence_after();
+  }
+  // the (last) layer's epilogue: N_out columns of the accumulator at TMEM column acc0
+  const int N_out = CHAIN ? N2 : N;
+  const uint32_t acc0 = CHAIN ? (uint32_t)N : 0u;
+  const float* const bias_out = CHAIN ? p.bias2 : p.bias;
+  constexpr int ACT_OUT = (CHAIN && EPI != TSD_EPI_DOT) ? TSD_ACT_NONE : ACT;
+  const int cols_per_half = N_out / NSL;
   constexpr int TLD = 36;  // padded row stride (floats) of the transpose tile: conflict-free float4 access
   float* tile = reinterpret_cast<float*>(smem_gen) + warp * (32 * TLD);
   float cscale = 1.f;
   if (EPI == TSD_EPI_SCALE && live) cscale = tsd_cutoff_fn(p.scale_len[m], p.cutoff, p.smooth);
   const float* emb_row = nullptr;
-  if (EPI == TSD_EPI_MULEMB) emb_row = p.mul_emb + (size_t)(live ? (p.mul_code[m] & 0xffff) : 0) * N;
+  if (EPI == TSD_EPI_MULEMB) emb_row = p.mul_emb + (size_t)(live ? (p.mul_code[m] & 0xffff) : 0) * N_out;
   float dot = 0.f;
   for (int cc = 0; cc < cols_per_half; cc += 32) {
     const int c0 = half * cols_per_half + cc;
     uint32_t v[32];
-    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc0 + (uint32_t)c0, v);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 b = bias_out ? __ldg(reinterpret_cast<const float4*>(bias_out + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 o;
-      o.x = tc_act<ACT>(__uint_as_float(v[j + 0]) + b.x);
-      o.y = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
-      o.z = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
-      o.w = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+      o.x = tc_act<ACT_OUT>(__uint_as_float(v[j + 0]) + b.x);
+      o.y = tc_act<ACT_OUT>(__uint_as_float(v[j + 1]) + b.y);
+      o.z = tc_act<ACT_OUT>(__uint_as_float(v[j + 2]) + b.z);
+      o.w = tc_act<ACT_OUT>(__uint_as_float(v[j + 3]) + b.w);
       if (EPI == TSD_EPI_SCALE) {
         o.x *= cscale; o.y *= cscale; o.z *= cscale; o.w *= cscale;
       }
@@ -304,19 +375,20 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
   }
 }
 
-template <int ACT, int EPI, int AKIND, int NT>
+template <int ACT, int EPI, int AKIND, int NT, bool CHAIN = false>
 int tc_launch_nt(const GemmArgs& g0, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
-                 cudaStream_t stream) {
+                 const CUtensorMap& map_w2, cudaStream_t stream) {
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI, AKIND, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TSD_CUDA(cudaFuncSetAttribute(k_gemm_tf32<ACT, EPI, AKIND, NT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
     attr_set = true;
   }
   smem = (size_t)tc_stages(NT) * (TC_A_PANEL_BYTES + (size_t)g0.N * TC_BK * 4) + 1024;
   const size_t tiles = (size_t)(NT / 32) * 32 * 36 * sizeof(float) + 1024;  // epilogue transpose tiles reuse the pipeline
   if (smem < tiles) smem = tiles;
-  TSD_CUDA(launch_pdl(k_gemm_tf32<ACT, EPI, AKIND, NT>, dim3(tsd_ceil_div(g0.M_cap, TC_BM)), dim3(NT), smem, stream, g0,
-                      tmem_cols, map_a, map_w));
+  TSD_CUDA(launch_pdl(k_gemm_tf32<ACT, EPI, AKIND, NT, CHAIN>, dim3(tsd_ceil_div(g0.M_cap, TC_BM)), dim3(NT), smem, stream,
+                      g0, tmem_cols, map_a, map_w, map_w2));
   TSD_LAUNCH_CHECK();
   return TSD_OK;
 }
@@ -327,8 +399,8 @@ template <int ACT, int EPI, int AKIND>
 int tc_launch(const GemmArgs& g, int tmem_cols, size_t smem, const CUtensorMap& map_a, const CUtensorMap& map_w,
               cudaStream_t stream) {
   const bool wide = g.N >= 128 && tsd_ceil_div(g.M_cap, TC_BM) <= 148;
-  if (wide) return tc_launch_nt<ACT, EPI, AKIND, 512>(g, tmem_cols, smem, map_a, map_w, stream);
-  return tc_launch_nt<ACT, EPI, AKIND, 256>(g, tmem_cols, smem, map_a, map_w, stream);
+  if (wide) return tc_launch_nt<ACT, EPI, AKIND, 512>(g, tmem_cols, smem, map_a, map_w, map_w, stream);
+  return tc_launch_nt<ACT, EPI, AKIND, 256>(g, tmem_cols, smem, map_a, map_w, map_w, stream);
 }
 
 template <int EPI, int AKIND>
@@ -385,6 +457,39 @@ int tsd_gemm_tf32(const GemmArgs& g, cudaStream_t stream) {
       return TSD_ERR_UNSUPPORTED;
   }
 #undef TC_GO
+}
+
+// Two chained layers on one tile (GemmArgs.W2): the computed-operand kernels of the edge embedding (cat0 -> cat2) and of
+// the pair MLP (l0 -> l1 -> row-dot).  One 512-thread CTA per SM (the two accumulators take all 512 TMEM columns).
+template <int EPI, int AKIND>
+static int tc_chain_dispatch(const GemmArgs& g, const CUtensorMap& map_w, const CUtensorMap& map_w2, cudaStream_t stream) {
+  switch (g.act) {
+    case TSD_ACT_NONE: return tc_launch_nt<TSD_ACT_NONE, EPI, AKIND, 512, true>(g, 512, 0, map_w, map_w, map_w2, stream);
+    case TSD_ACT_RELU: return tc_launch_nt<TSD_ACT_RELU, EPI, AKIND, 512, true>(g, 512, 0, map_w, map_w, map_w2, stream);
+    case TSD_ACT_SWISH: return tc_launch_nt<TSD_ACT_SWISH, EPI, AKIND, 512, true>(g, 512, 0, map_w, map_w, map_w2, stream);
+    case TSD_ACT_SSP: return tc_launch_nt<TSD_ACT_SSP, EPI, AKIND, 512, true>(g, 512, 0, map_w, map_w, map_w2, stream);
+    default: return TSD_ERR_UNSUPPORTED;
+  }
+}
+
+int tsd_gemm_chain2_tf32(const GemmArgs& g, cudaStream_t stream) {
+  if (!g.W2 || g.N != 256 || !(g.N2 == 128 || g.N2 == 256) || g.K % TC_BK != 0 || g.K < 4 * TC_BK || g.M_cap < 1024)
+    return TSD_ERR_UNSUPPORTED;
+  if (!(g.a_kind == TSD_A_CAT || g.a_kind == TSD_A_PAIR) || g.residual) return TSD_ERR_UNSUPPORTED;
+  TSD_REQUIRE(g.W && g.A && (g.out_vec || g.C));
+  const int epi = tsd_gemm_epi_kind(g);
+  if (!(epi == TSD_EPI_PLAIN || epi == TSD_EPI_DOT)) return TSD_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g.W) | reinterpret_cast<uintptr_t>(g.W2)) & 15) return TSD_ERR_UNSUPPORTED;
+  CUtensorMap map_w, map_w2;
+  if (!make_tensor_map(&map_w, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint32_t)g.N) ||
+      !make_tensor_map(&map_w2, g.W2, (uint64_t)g.N2, (uint64_t)g.N, (uint32_t)g.N2))
+    return TSD_ERR_UNSUPPORTED;
+  if (g.a_kind == TSD_A_CAT) {
+    if (epi == TSD_EPI_PLAIN) return tc_chain_dispatch<TSD_EPI_PLAIN, TSD_A_CAT>(g, map_w, map_w2, stream);
+    return TSD_ERR_UNSUPPORTED;
+  }
+  if (epi == TSD_EPI_DOT) return tc_chain_dispatch<TSD_EPI_DOT, TSD_A_PAIR>(g, map_w, map_w2, stream);
+  return TSD_ERR_UNSUPPORTED;
 }
 
 // elementwise round-to-nearest fp32 -> TF32 (kept in an fp32 container): weight shadow copies
