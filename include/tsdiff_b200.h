@@ -224,12 +224,16 @@ int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edges, const f
  * the next aggregation.  h_in is not modified; h_out may not alias h_in.
  * ef_pool (optional): ef_pool_count x (E_cap, H) extra filter buffers.  The filter network of a block only depends
  * on edge_attr, so with one buffer per block (2 + ef_pool_count >= num_blocks) the edge-side kernels of ALL blocks
- * run ahead of the serial node-side chain instead of waiting for the block that last used their buffer. */
+ * run ahead of the serial node-side chain instead of waiting for the block that last used their buffer.
+ * x1_first (optional, tf32 fast path only): an (N, H) buffer for the first block's x1 = lin1_0(h_in).  With
+ * x1_first_valid = 0 the encoder computes it into the buffer, with 1 it trusts the buffer: a caller whose h_in does not
+ * change between calls (the Langevin loop: the node embedding is position independent, the reference recomputes
+ * lin1(h) every step, schnet.py:101) takes that kernel out of every step. */
 int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                        const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
                        float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* nf_pool,
-                       int32_t nf_pool_count, float* ef_pool, int32_t ef_pool_count, int32_t math,
-                       tsd_stream_t stream);
+                       int32_t nf_pool_count, float* ef_pool, int32_t ef_pool_count, float* x1_first,
+                       int32_t x1_first_valid, int32_t math, tsd_stream_t stream);
 
 /* The node side of one InteractionBlock as ONE tensor-core kernel (tf32; what tsd_schnet_encoder launches per block when
  * the batch has few atoms -- schnet.py:101-104,124-128 and the next block's :101):

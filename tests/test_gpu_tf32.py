@@ -130,6 +130,36 @@ def test_condensenc_forward_tf32_batch100_chained_kernels():
     assert 1e-7 < err < 3e-3, err
 
 
+@pytest.mark.parametrize("network", ["condensenc", "dualenc"])
+def test_chained_two_layer_gemm_equals_separate_kernels(network):
+    """cat0 -> cat2 of the edge embedding (and its second-graph delta rows) and l0 -> l1 -> row-dot of the pair MLP run as
+    ONE tensor-core kernel with the first layer's output kept in tensor memory (k_gemm_tf32<..., CHAIN>).  Same operands,
+    same rounding points, same accumulation order as the two separate kernels: the edge scores must be bit-identical
+    with the chaining switched off (the library's tuning hook)."""
+    from tsdiff_b200.synthetic import make_batch
+    g = make_batch(100, seed=5)
+    m = make_model(network, 0, DEV)
+    m.math = "tf32"
+    d = to_dev(g, DEV)
+    pos = (g["pos_init"] * 4.0).to(DEV)
+    lib = L.load()
+    out = {}
+    try:
+        for on in (1, 0):
+            lib.tsd_tune_gemm_chain2(on)
+            if network == "condensenc":
+                o = m(d["atom_type"], d["r_feat"], d["p_feat"], pos, d["bond_index"], d["bond_type"], d["batch"], None)
+                out[on] = [o[0].clone()]
+            else:
+                o = m(d["atom_type"], pos, d["bond_index"], d["bond_type"], d["batch"], None, return_edges=True)
+                out[on] = [o[0].clone(), o[1].clone()]
+            torch.cuda.synchronize()
+    finally:
+        lib.tsd_tune_gemm_chain2(1)
+    for a, b in zip(out[1], out[0]):
+        assert a.abs().max() > 0 and torch.equal(a, b)
+
+
 def test_dualenc_forward_tf32_batch100():
     """Path A at config-2 size (H = 128 chained kernels + GIN layers): tf32 vs fp32 FFMA path."""
     from tsdiff_b200.synthetic import make_batch

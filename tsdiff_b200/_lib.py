@@ -102,7 +102,7 @@ _SIGNATURES = {
     "tsd_filter_network": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Interaction), _P, _P, C.c_int32, _P],
     "tsd_filter_stack": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Interaction), C.c_int32, C.POINTER(C.c_void_p), _P],
     "tsd_schnet_encoder": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Interaction), C.c_int32, _P, _P, _P, _P,
-                           _P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P],
+                           _P, _P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P],
     "tsd_interaction_node_update": [C.POINTER(Batch), C.POINTER(Edges), C.POINTER(Interaction), C.POINTER(Linear), _P, _P, _P,
                                     _P, _P, _P],
     "tsd_gine_layer": [C.POINTER(Batch), C.POINTER(Edges), _P, C.POINTER(Gine), _P, _P, _P, _P, C.c_int32, _P],

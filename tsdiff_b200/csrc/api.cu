@@ -524,9 +524,9 @@ extern "C" int tsd_filter_network(const tsd_batch_t* batch, const tsd_edges_t* e
 // The filter networks of blocks [0, num_blocks) in ONE kernel (filter_stack.cu; tf32 only): filt[l] = nn2_l(ssp(nn0_l(
 // edge_attr))) * C_l(len).  TSD_ERR_UNSUPPORTED when the shapes do not fit the kernel (callers fall back to one
 // tsd_filter_network per block).
-extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
-                                const tsd_interaction_t* blocks, int32_t num_blocks, float* const* filt,
-                                tsd_stream_t stream) {
+static int filter_stack_launch(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                               const tsd_interaction_t* blocks, int32_t num_blocks, float* const* filt, int max_ctas,
+                               tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && edge_attr && blocks && filt && num_blocks >= 1);
   if (num_blocks > TSD_FS_MAX_LAYERS) return TSD_ERR_UNSUPPORTED;
   const int H = blocks[0].nn2.out_features;
@@ -538,6 +538,7 @@ extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edg
   a.num_layers = num_blocks;
   a.A = edge_attr;
   a.len = edges->length;
+  a.max_ctas = max_ctas;
   for (int l = 0; l < num_blocks; ++l) {
     const tsd_interaction_t& b = blocks[l];
     if (b.nn0.in_features != H || b.nn0.out_features != H || b.nn2.in_features != H || b.nn2.out_features != H)
@@ -554,9 +555,16 @@ extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edg
   return tsd_filter_stack_tf32(a, tsd_cu(stream));
 }
 
+extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
+                                const tsd_interaction_t* blocks, int32_t num_blocks, float* const* filt,
+                                tsd_stream_t stream) {
+  return filter_stack_launch(batch, edges, edge_attr, blocks, num_blocks, filt, 0, stream);
+}
+
 // tuning hook of profiles/scripts (not part of the C-ABI header): -1 = one filter kernel per block (round-2 path),
 // 0 = all blocks in one launch, k > 0 = two launches, blocks [0, k) and [k, L)
-static int g_filter_stack_mode = 0;
+static int g_filter_stack_mode = 0, g_filter_stack_ctas2 = 0;
+extern "C" void tsd_tune_filter_stack_ctas2(int ctas) { g_filter_stack_ctas2 = ctas; }
 // programmatic dependent launch of the edge-side GEMM kernels (gemm_tc.cu, gemm_chain.cu)
 int g_tsd_gemm_pdl = 1;
 extern "C" void tsd_tune_gemm_pdl(int on) { g_tsd_gemm_pdl = on; }
@@ -568,8 +576,8 @@ extern "C" void tsd_tune_filter_stack(int code) { g_filter_stack_mode = code; }
 extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* edges, const float* edge_attr,
                                   const tsd_interaction_t* blocks, int32_t num_blocks, const float* h_in, float* h_out,
                                   float* ef0, float* ef1, float* nf0, float* nf1, float* nf2, float* nf_pool,
-                                  int32_t nf_pool_count, float* ef_pool, int32_t ef_pool_count, int32_t math,
-                                  tsd_stream_t stream) {
+                                  int32_t nf_pool_count, float* ef_pool, int32_t ef_pool_count, float* x1_first,
+                                  int32_t x1_first_valid, int32_t math, tsd_stream_t stream) {
   TSD_REQUIRE(batch && edges && edge_attr && blocks && num_blocks >= 1 && h_in && h_out && ef0 && ef1 && nf0 && nf1 && nf2);
   cudaStream_t s = tsd_cu(stream);
   const int H = blocks[0].lin.out_features;
@@ -636,7 +644,8 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     na.x = h_in;  // x1 of block 0
     na.num_stages = 1;
     na.st[0].W = blocks[0].lin1.weight;
-    na.st[0].store = x1buf[0];
+    float* const x1_block0 = x1_first ? x1_first : x1buf[0];
+    na.st[0].store = x1_block0;
     // With one filter buffer per block the filter networks of all blocks run as ONE kernel (filter_stack.cu) -- or as
     // two launches, so that the node chain starts after the first few blocks' filters -- ahead of the node side.
     bool stacked = g_filter_stack_mode >= 0 && nbuf >= num_blocks && num_blocks <= TSD_FS_MAX_LAYERS;
@@ -650,7 +659,8 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
         TSD_TRY(rc);
         TSD_CUDA(cudaEventRecord(fk.edge_done[0], s));
         if (stack_cut < num_blocks) {
-          TSD_TRY(tsd_filter_stack(batch, edges, edge_attr, blocks + stack_cut, num_blocks - stack_cut, fbuf + stack_cut, stream));
+          TSD_TRY(filter_stack_launch(batch, edges, edge_attr, blocks + stack_cut, num_blocks - stack_cut, fbuf + stack_cut,
+                                      g_filter_stack_ctas2, stream));
           TSD_CUDA(cudaEventRecord(fk.edge_done[stack_cut], s));
         }
       }
@@ -658,7 +668,8 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     // Node kernel shape: behind the filter stack the node chain has the GPU to itself, so two CTAs share a 32-atom tile's
     // gathers; next to per-block filter kernels one CTA per tile competes least for SMs (profiles/r3_stack_modes.txt).
     int npc0 = 0;
-    TSD_TRY(tsd_node_update_tf32(na, tsd_node_tile(false, batch->num_nodes, &npc0), side));  // x1 of block 0: dense input
+    if (!(x1_first && x1_first_valid))  // x1 of block 0: dense input (skipped when the caller holds it from an earlier call)
+      TSD_TRY(tsd_node_update_tf32(na, tsd_node_tile(false, batch->num_nodes, &npc0), side));
     const int tile = tsd_node_tile(stacked && stack_cut == num_blocks, batch->num_nodes, &npc);
     for (int l = 0; l < num_blocks; ++l) {
       const tsd_interaction_t& b = blocks[l];
@@ -691,7 +702,7 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
       na.in_ptr = edges->in_ptr;
       na.in_eid = edges->in_eid;
       na.in_src = edges->in_src;
-      na.x1 = x1buf[l & 1];
+      na.x1 = l == 0 ? x1_block0 : x1buf[l & 1];
       na.filt = filt;
       na.st[0].W = b.lin2.weight;
       na.st[0].bias = b.lin2.bias;

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
 }
 
 template <int H>
-int fs_launch(const FsArgsDev& d, const FilterStackMaps& maps, cudaStream_t stream) {
+int fs_launch(const FsArgsDev& d, const FilterStackMaps& maps, int max_ctas, cudaStream_t stream) {
   constexpr int SLOT = H * TC_BK * 4 + TC_A_PANEL_BYTES;
   const int budget = 227 * 1024 - 1024 - FS_STAGE_BYTES - 256;  // alignment slack, staging, barriers
   int slots = budget / SLOT;
@@ -334,7 +334,8 @@ int fs_launch(const FsArgsDev& d, const FilterStackMaps& maps, cudaStream_t stre
     TSD_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int max_items = tsd_ceil_div(d.M_cap, TC_BM) * d.num_layers;
-  const int grid = g_fs_grid > 0 ? g_fs_grid : (max_items < num_sms ? max_items : num_sms);
+  int grid = g_fs_grid > 0 ? g_fs_grid : (max_items < num_sms ? max_items : num_sms);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   k_filter_stack<H><<<dim3(grid), dim3(FS_THREADS), smem, stream>>>(d, maps, slots);
   TSD_LAUNCH_CHECK();
   return TSD_OK;
@@ -377,5 +378,5 @@ int tsd_filter_stack_tf32(const FilterStackArgs& a, cudaStream_t stream) {
     d.layer[l].cutoff = y.cutoff;
     d.layer[l].smooth = y.smooth;
   }
-  return a.H == 256 ? fs_launch<256>(d, maps, stream) : fs_launch<128>(d, maps, stream);
+  return a.H == 256 ? fs_launch<256>(d, maps, a.max_ctas, stream) : fs_launch<128>(d, maps, a.max_ctas, stream);
 }

@@ -191,6 +191,7 @@ struct FilterStackArgs {
   int H, num_layers;
   const float* A;    // edge_attr (M_cap, H)
   const float* len;  // (M_cap)
+  int max_ctas;      // 0 = one CTA per SM; otherwise at most this many (a launch that shares the GPU with the node chain)
   FilterStackLayer layer[TSD_FS_MAX_LAYERS];
 };
 int tsd_filter_stack_tf32(const FilterStackArgs& a, cudaStream_t stream);

@@ -362,7 +362,11 @@ class CondensedScoreEngine:
                                              L_act(cfg.edge_cat_act), self.wv)
             blocks = _interaction_array(_interaction_structs(m.encoder.interactions, self.wv))
             pair = _pair_mlp_struct(m.grad_dist_mlp, self.wv)
-            self.members.append({"z": z, "enc": enc, "keep": keep, "blocks": blocks, "pair": pair})
+            # x1 of the first interaction block = lin1_0(z): position independent like z; the encoder fills it on the
+            # first evaluation and skips the kernel afterwards (tsd_schnet_encoder's x1_first)
+            x1_first = torch.empty(max(plan.num_nodes, 1), h, dtype=torch.float32, device=plan.device)
+            self.members.append({"z": z, "enc": enc, "keep": keep, "blocks": blocks, "pair": pair, "x1_first": x1_first,
+                                 "x1_valid": 0})
 
     @_on_plan_device
     def evaluate(self, pos):
@@ -385,8 +389,10 @@ class CondensedScoreEngine:
             L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea1), mem["blocks"], len(mem["blocks"]), L.ptr(mem["z"]),
                                            L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
                                            L.ptr(self.nf_pool), self.nf_pool_count, L.ptr(self.ef_pool),
-                                           self.ef_pool_count, self.math, s),
+                                           self.ef_pool_count, L.ptr(mem["x1_first"]), mem["x1_valid"], self.math, s),
                     "tsd_schnet_encoder")
+            if not torch.cuda.is_current_stream_capturing():
+                mem["x1_valid"] = 1  # a call baked into a CUDA graph has to recompute it on every replay
             if self.two_graphs:
                 # the pred_edge_order graph's edge embedding only needs d_emb and is only read by the pair
                 # MLP: a side stream (a graph branch under capture) lets it fill the SMs the encoder leaves
@@ -477,6 +483,9 @@ class DualScoreEngine:
         self.local_scratch = ([torch.empty(cap, h, dtype=torch.float32, device=plan.device) for _ in range(2)]
                               if self.ts else [None, None])
         self.edge_inv_global = torch.zeros(cap, dtype=torch.float32, device=plan.device)
+        # lin1 of the first global interaction block applied to the (position independent) node embedding
+        self.x1_first = torch.empty(max(plan.num_nodes, 1), h, dtype=torch.float32, device=plan.device)
+        self.x1_valid = 0
         self.edge_inv_local = torch.zeros(cap, dtype=torch.float32, device=plan.device)
         self.atom_type = atom_type.to(torch.long).contiguous()
         act = model.edge_encoder_global.mlp.act
@@ -539,7 +548,9 @@ class DualScoreEngine:
         L.check(lib.tsd_schnet_encoder(b, e, L.ptr(ea_g), self.blocks, len(self.blocks), L.ptr(self.h0_global),
                                        L.ptr(hbuf), L.ptr(ef0), L.ptr(ef1), L.ptr(nf0), L.ptr(nf1), L.ptr(nf2),
                                        L.ptr(self.nf_pool), self.nf_pool_count, L.ptr(self.ef_pool), self.ef_pool_count,
-                                       self.math, s), "tsd_schnet_encoder")
+                                       L.ptr(self.x1_first), self.x1_valid, self.math, s), "tsd_schnet_encoder")
+        if not torch.cuda.is_current_stream_capturing():
+            self.x1_valid = 1
         L.check(lib.tsd_pair_mlp(b, e, L.ptr(hbuf), L.ptr(ea_g), C.byref(self.pair_g), 0, L.ptr(ef0),
                                  L.ptr(self.edge_inv_global), self.math, s), "tsd_pair_mlp")
         main.wait_stream(self.side)
