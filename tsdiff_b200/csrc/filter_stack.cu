@@ -16,8 +16,8 @@
 //                panel by panel as soon as the epilogue warps have produced the matching QUARTER of X.
 //   warps 0..15  epilogues.  epi1: acc1 -> + b0 -> shifted softplus -> TF32 (RNE) -> written back IN PLACE over
 //                acc1 (tcgen05.st): X never leaves tensor memory, the second GEMM takes its A operand from
-//                TMEM.  Handed to the MMA issuer in four column quarters, so the second GEMM trails the
-//                activation by a quarter instead of waiting for all of it.
+//                TMEM.  Handed to the MMA issuer K panel by K panel (32 columns), so the second GEMM trails the
+//                activation by a panel instead of waiting for all of it.
 //   warps 18..25 epi2 (two warps per TMEM lane quarter = 32 rows, even / odd output panels): acc2 -> + b2 -> * C(len)
 //                -> 32 x 32 block in the warp's own 4 KiB staging -> TMA store (1.2 us per block: the stores queue
 //                behind the weight loads of the same SM; reading the block back and storing whole 128-byte lines
@@ -81,7 +81,7 @@ struct FsBars {
   uint64_t full[FS_MAX_SLOTS];
   uint64_t empty[FS_MAX_SLOTS];
   uint64_t acc1_full, acc2_full, acc2_free;
-  uint64_t x_ready[4];
+  uint64_t x_ready[8];  // one per K panel of X
   uint32_t tmem_base;
 };
 
@@ -126,9 +126,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
   constexpr int NKB = H / TC_BK;                 // K panels per GEMM = 32-column panels of the output
   constexpr int W_PANEL = H * TC_BK * 4;         // bytes of one W panel: H rows x 128 B
   constexpr int SLOT = W_PANEL + TC_A_PANEL_BYTES;
-  constexpr int CQ = H / 16;                     // accumulator columns per epilogue warp and quarter
-  constexpr int KBQ = NKB / 4;                   // K panels per quarter of X
-  static_assert(NKB % 4 == 0 && (CQ == 8 || CQ == 16), "H must be 128 or 256");
+  constexpr int CQ = TC_BK / 4;                  // X is handed over panel by panel: 8 of its 32 columns per activation warp
+  static_assert(NKB <= 8 && NKB % 4 == 0, "H must be 128 or 256");
   extern __shared__ uint8_t smem_dyn[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -154,7 +153,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
     mbar_init(&bars->acc1_full, 1);
     mbar_init(&bars->acc2_full, 1);
     mbar_init(&bars->acc2_free, FS_STORE_WARPS);
-    for (int t = 0; t < 4; ++t) mbar_init(&bars->x_ready[t], FS_EPI_THREADS);
+    for (int t = 0; t < NKB; ++t) mbar_init(&bars->x_ready[t], FS_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[0])) : "memory");
@@ -216,17 +215,16 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
         }
         umma_commit(&bars->acc1_full);
         FS_STAMP(16 * l + 10);
-        // acc2 = X . W2^T, a quarter of X (KBQ panels) at a time, once the store warps have read the previous layer's acc2
+        // acc2 = X . W2^T, panel by panel of X as the activation warps hand them over, once the store warps have read the
+        // previous item's acc2
         if (it > 0) {
           mbar_wait(&bars->acc2_free, (uint32_t)((it - 1) & 1));
           tc_fence_after();
         }
         for (int kb = 0; kb < NKB; ++kb, ++g) {
-          if (kb % KBQ == 0) {
-            mbar_wait(&bars->x_ready[kb / KBQ], (uint32_t)(it & 1));
-            tc_fence_after();
-            if (kb == 0) FS_STAMP(16 * l + 11);
-          }
+          mbar_wait(&bars->x_ready[kb], (uint32_t)(it & 1));
+          tc_fence_after();
+          if (kb == 0) FS_STAMP(16 * l + 11);
           const int s = g % num_slots, round = g / num_slots;
           mbar_wait(&bars->full[s], (uint32_t)(round & 1));
           tc_fence_after();
@@ -245,18 +243,18 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
     for (int item = blockIdx.x; item < items; item += stride, ++it) {
       const int l = item / tiles;
       const float* const b0 = p.layer[l].b0;
-      // X = tf32(ssp(acc1 + b0)), in place, quarter by quarter
+      // X = tf32(ssp(acc1 + b0)), in place, one K panel of the second GEMM at a time
       mbar_wait(&bars->acc1_full, (uint32_t)(it & 1));
       tc_fence_after();
       if (tid == 0) FS_STAMP(16 * l + 0);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int c0 = t * (H / 4) + cg * CQ;
+      for (int t = 0; t < NKB; ++t) {
+        const int c0 = t * TC_BK + cg * CQ;
         fs_activate_in_place<CQ>(acc1 + lane_addr + (uint32_t)c0, b0 ? b0 + c0 : nullptr);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->x_ready[t]);
-        if (tid == 0) FS_STAMP(16 * l + 1 + t);
+        if (tid == 0 && (t & 1)) FS_STAMP(16 * l + 1 + (t >> 1));
       }
     }
   } else {

@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       }
       const int* eids = staged ? s_eid - seg0 : p.in_eid;
       const int* srcs = staged ? s_src - seg0 : p.in_src;
-      const uint32_t x_own = nu_mapa(smem_base, rank), x_peer = nu_mapa(smem_base, peer);
+      const uint32_t x_own = smem_base, x_peer = nu_mapa(smem_base, peer);  // own copy: plain shared-memory stores
       pdl_wait();  // see k_node_update
       pdl_trigger();
       if (tid == 0) NU_STAMP(7);
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
         if (node0 + my0 + n < N) acc = nu_aggregate_item(p, eids, srcs, s_ptr[n], s_ptr[n + 1], off, lane);
         const float4 r = tf32_rn4(acc);
         const uint32_t o = (uint32_t)((off >> 5) * X_PANEL) + sw128_off(my0 + n, (off & 31) >> 2);
-        nu_st_cluster4(x_own + o, r);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(x_own + o), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
         nu_st_cluster4(x_peer + o, r);
       }
       // every thread fences its own writes, the workers meet, ONE thread publishes with cluster-scope release (instead of
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       tmem_ld_cols_async<CW>(taddr + (uint32_t)NT, v1);
       tmem_wait_ld();
       const uint32_t xo = (((s + 1) & 1) ? xbuf1 : xbuf0) + (uint32_t)((f >> 5) * X_PANEL + ((f & 3) << 2));
-      const uint32_t x_own = nu_mapa(xo, rank), x_peer = nu_mapa(xo, peer);
+      const uint32_t x_own = xo, x_peer = nu_mapa(xo, peer);  // own copy: plain shared-memory stores
       const int chunk = (f & 31) >> 2;
       float r[CW];
 #pragma unroll
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
           const int n = n0 + j;
           const uint32_t o = (uint32_t)(n * 128 + ((chunk ^ (n & 7)) << 4));
           const float t = tf32_rn(r[j]);
-          nu_st_cluster1(x_own + o, t);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_own + o), "f"(t) : "memory");
           nu_st_cluster1(x_peer + o, t);
         }
         asm volatile("fence.proxy.async;" ::: "memory");
