@@ -574,8 +574,12 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       const bool staged = seg_n <= CAP;
       if (staged) {
         for (int i = tid; i < seg_n; i += NW) {
-          s_eid[i] = p.in_eid[seg0 + i];
+          const int e = p.in_eid[seg0 + i];
+          s_eid[i] = e;
           s_src[i] = p.in_src[seg0 + i];
+          // the filter rows were written by the filter stack tens of microseconds (and ~90 MB) ago: pull them back
+          // into L2 while the preceding node kernel is still running (profiles/r3_pair_gather_cost.txt)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.filt + (size_t)e * H), "r"(H * 4) : "memory");
         }
         asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
       }
