@@ -1,6 +1,6 @@
 """Langevin-step time (CUDA-graph replays, late-trajectory edge count) for the filter-stack launch modes and node tiles
 in ONE process: the tuning hooks are run-time switches, every mode re-captures its graph.
-usage: python profiles/scripts/stack_modes.py [mode:tile[:pdl[:stack_ctas[:gemm_pdl[:atoms_per_node_cluster[:chain2[:stack2_ctas]]]]]] ...]   (mode -1 = one filter kernel per block)"""
+usage: python profiles/scripts/stack_modes.py [mode:tile[:pdl[:stack_ctas[:gemm_pdl[:atoms_per_node_cluster[:chain2[:stack2_ctas[:node_chain]]]]]]] ...]   (mode -1 = one filter kernel per block)"""
 import sys, json, torch
 sys.path.insert(0, '.')
 import bench
@@ -29,6 +29,8 @@ for spec in specs:
     lib.tsd_tune_gemm_chain2(chain2)
     ctas2 = f[7] if len(f) > 7 else 0
     lib.tsd_tune_filter_stack_ctas2(ctas2)
+    nchain = f[8] if len(f) > 8 else 1
+    lib.tsd_tune_node_chain(nchain)
     lib.tsd_tune_filter_stack(mode)
     lib.tsd_tune_node_tile(tile)
     torch.manual_seed(0)
@@ -39,10 +41,11 @@ for spec in specs:
     t0.record()
     for _ in range(1500): runner.graph.replay()
     t1.record(); torch.cuda.synchronize()
-    out = {"mode": mode, "tile": tile, "pdl": pdl, "stack_ctas": grid, "gemm_pdl": gpdl, "npc": npc, "chain2": chain2, "stack2_ctas": ctas2, "step_us": t0.elapsed_time(t1) / 1500 * 1e3,
+    out = {"mode": mode, "tile": tile, "pdl": pdl, "stack_ctas": grid, "gemm_pdl": gpdl, "npc": npc, "chain2": chain2, "stack2_ctas": ctas2, "node_chain": nchain, "step_us": t0.elapsed_time(t1) / 1500 * 1e3,
            "pairs": eng.plan.work_count()}
     if pos is not None:
         if ref_pos is None: ref_pos = pos
         out["max_abs_pos_diff_vs_first_mode"] = float((pos - ref_pos).abs().max())
+    out["node_chain_flag"] = lib.tsd_node_chain_flag()
     print(json.dumps(out), flush=True)
     del eng, runner

@@ -160,6 +160,36 @@ def test_chained_two_layer_gemm_equals_separate_kernels(network):
         assert a.abs().max() > 0 and torch.equal(a, b)
 
 
+def test_persistent_node_chain_equals_per_block_kernels():
+    """Behind the filter stack the node side of all interaction blocks runs as ONE persistent kernel (k_node_chain: grid
+    barrier between blocks, the next block's filter rows landed in shared memory while a CTA waits).  Same gathers in the
+    same order, same GEMMs: the edge scores must be bit-identical with one k_node_pair launch per block (tuning hook),
+    over repeated evaluations (the barrier counter is reset by every launch), and the barrier must never time out."""
+    from tsdiff_b200.synthetic import make_batch
+    g = make_batch(100, seed=6)
+    m = make_model("condensenc", 0, DEV)
+    m.math = "tf32"
+    d = to_dev(g, DEV)
+    lib = L.load()
+    out = {}
+    try:
+        for on in (1, 0, 1):
+            lib.tsd_tune_node_chain(on)
+            res = []
+            for scale in (4.0, 3.0):
+                pos = (g["pos_init"] * scale).to(DEV)
+                o = m(d["atom_type"], d["r_feat"], d["p_feat"], pos, d["bond_index"], d["bond_type"], d["batch"], None)
+                res.append(o[0].clone())
+            torch.cuda.synchronize()
+            out.setdefault(on, []).append(res)
+    finally:
+        lib.tsd_tune_node_chain(1)
+    assert lib.tsd_node_chain_flag() == 0
+    for res in out[1]:
+        for a, b in zip(res, out[0][0]):
+            assert a.abs().max() > 0 and torch.isfinite(a).all() and torch.equal(a, b)
+
+
 def test_dualenc_forward_tf32_batch100():
     """Path A at config-2 size (H = 128 chained kernels + GIN layers): tf32 vs fp32 FFMA path."""
     from tsdiff_b200.synthetic import make_batch

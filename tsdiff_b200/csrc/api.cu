@@ -449,9 +449,15 @@ struct EncoderFork {
   cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, xh_init = nullptr;
   cudaEvent_t edge_done[MAX_BLOCKS], agg_done[MAX_BLOCKS], n2_done[MAX_BLOCKS];
   bool ready = false;
+  unsigned int* nc_words = nullptr;  // node chain (node_chain.cu): [0] grid barrier counter, [1] error flag
   int init(int num_blocks) {
     if (num_blocks > MAX_BLOCKS) return TSD_ERR_UNSUPPORTED;
     if (ready) return TSD_OK;
+    // (a first call under stream capture cannot allocate: the node chain then stays one kernel per block)
+    if (cudaMalloc(&nc_words, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(nc_words, 0, 8) != cudaSuccess) {
+      (void)cudaGetLastError();
+      nc_words = nullptr;
+    }
     // the node-side chain is serial and short (15-CTA kernels): give it the highest priority so its
     // CTAs are scheduled as soon as an SM frees up instead of queueing behind the edge tiles
     int prio_lo = 0, prio_hi = 0;
@@ -563,7 +569,15 @@ extern "C" int tsd_filter_stack(const tsd_batch_t* batch, const tsd_edges_t* edg
 
 // tuning hook of profiles/scripts (not part of the C-ABI header): -1 = one filter kernel per block (round-2 path),
 // 0 = all blocks in one launch, k > 0 = two launches, blocks [0, k) and [k, L)
-static int g_filter_stack_mode = 0, g_filter_stack_ctas2 = 0;
+static int g_filter_stack_mode = 0, g_filter_stack_ctas2 = 0, g_node_chain = 0;
+extern "C" void tsd_tune_node_chain(int on) { g_node_chain = on; }
+static unsigned int* g_nc_words_for_flag = nullptr;
+// debugging aid: the persistent node chain's error flag (4 = its grid barrier timed out); synchronises the device
+extern "C" int tsd_node_chain_flag(void) {
+  unsigned int v = 0;
+  if (g_nc_words_for_flag && cudaMemcpy(&v, g_nc_words_for_flag + 1, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int)v;
+}
 extern "C" void tsd_tune_filter_stack_ctas2(int ctas) { g_filter_stack_ctas2 = ctas; }
 // programmatic dependent launch of the edge-side GEMM kernels (gemm_tc.cu, gemm_chain.cu)
 int g_tsd_gemm_pdl = 1;
@@ -671,6 +685,45 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     if (!(x1_first && x1_first_valid))  // x1 of block 0: dense input (skipped when the caller holds it from an earlier call)
       TSD_TRY(tsd_node_update_tf32(na, tsd_node_tile(false, batch->num_nodes, &npc0), side));
     const int tile = tsd_node_tile(stacked && stack_cut == num_blocks, batch->num_nodes, &npc);
+    // Behind the complete filter stack the node side of ALL blocks is one persistent kernel (node_chain.cu) when every
+    // cluster can be resident at once; otherwise one node kernel per block below.
+    if (stacked && stack_cut == num_blocks && tile == 323 && H == 256 && g_node_chain && fk.nc_words &&
+        num_blocks <= TSD_NC_MAX_BLOCKS) {
+      NodeChainArgs ca;
+      memset(&ca, 0, sizeof(ca));
+      ca.num_nodes = batch->num_nodes;
+      ca.H = H;
+      ca.num_blocks = num_blocks;
+      ca.nodes_per_cluster = npc;
+      ca.in_ptr = edges->in_ptr;
+      ca.in_eid = edges->in_eid;
+      ca.in_src = edges->in_src;
+      ca.x1_first = x1_block0;
+      ca.x1buf[0] = x1buf[0];
+      ca.x1buf[1] = x1buf[1];
+      ca.h_in = h_in;
+      ca.h_out = h_out;
+      ca.barrier = fk.nc_words;
+      ca.error_flag = reinterpret_cast<int*>(fk.nc_words + 1);
+      for (int l = 0; l < num_blocks; ++l) {
+        ca.blk[l].filt = fbuf[l];
+        ca.blk[l].w_lin2 = blocks[l].lin2.weight;
+        ca.blk[l].b_lin2 = blocks[l].lin2.bias;
+        ca.blk[l].w_lin = blocks[l].lin.weight;
+        ca.blk[l].b_lin = blocks[l].lin.bias;
+        ca.blk[l].w_lin1_next = l + 1 < num_blocks ? blocks[l + 1].lin1.weight : nullptr;
+      }
+      g_nc_words_for_flag = fk.nc_words;
+      TSD_CUDA(cudaStreamWaitEvent(side, fk.edge_done[0], 0));
+      TSD_CUDA(cudaMemsetAsync(fk.nc_words, 0, sizeof(unsigned int), side));
+      const int rc = tsd_node_chain_tf32(ca, side);
+      if (rc == TSD_OK) {
+        TSD_CUDA(cudaEventRecord(fk.join, side));
+        TSD_CUDA(cudaStreamWaitEvent(s, fk.join, 0));
+        return TSD_OK;
+      }
+      if (rc != TSD_ERR_UNSUPPORTED) return rc;
+    }
     for (int l = 0; l < num_blocks; ++l) {
       const tsd_interaction_t& b = blocks[l];
       float* filt = fbuf[l % nbuf];

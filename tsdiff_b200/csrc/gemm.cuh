@@ -174,6 +174,33 @@ struct NodeArgs {
   NodeStage st[3];
 };
 
+// the node side of ALL interaction blocks in one persistent kernel (node_chain.cu)
+constexpr int TSD_NC_MAX_BLOCKS = 8;
+struct NodeChainBlock {
+  const float* filt;   // (rows, H) filter of this block
+  const float* w_lin2; // (H, H) TF32-rounded shadows
+  const float* b_lin2;
+  const float* w_lin;
+  const float* b_lin;
+  const float* w_lin1_next;  // the NEXT block's lin1 (no bias); NULL for the last block
+};
+struct NodeChainArgs {
+  int num_nodes, H, num_blocks;
+  int nodes_per_cluster;     // atoms a cluster owns (<= 32); 0 = 32
+  const int* in_ptr;
+  const int* in_eid;
+  const int* in_src;
+  const float* x1_first;     // (N, H) x1 of block 0
+  float* x1buf[2];           // block l > 0 reads x1buf[l & 1]; block l writes x1buf[(l + 1) & 1]
+  const float* h_in;         // residual of block 0
+  float* h_out;              // written by every block, residual of the next one
+  unsigned int* barrier;     // grid barrier counter, zero at launch
+  int* error_flag;           // |= 4 if the grid barrier timed out (a CTA was never scheduled)
+  NodeChainBlock blk[TSD_NC_MAX_BLOCKS];
+};
+// TSD_ERR_UNSUPPORTED when the clusters cannot all be resident at once (callers launch one node kernel per block)
+int tsd_node_chain_tf32(const NodeChainArgs& a, cudaStream_t stream);
+
 // the CFConv filter networks of ALL interaction blocks on one 128-row tile, layer after layer (filter_stack.cu)
 constexpr int TSD_FS_MAX_LAYERS = 8;
 struct FilterStackLayer {

@@ -465,14 +465,20 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
   __shared__ uint64_t bar_x[3];    // B operand of stage s complete: one arrival per CTA, after its workers' barrier
   __shared__ uint64_t bar_acc[2];  // accumulator set b complete (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_ptr[NA + 1];
+  __shared__ int s_ptr[NA + 1];   // staged (local) positions of this CTA's atoms' in-edges
+  __shared__ int s_gbeg[NA];      // ... and where they start in the global in-CSR
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) NU_STAMP(0);
   const uint32_t rank = nu_cluster_rank();
+  // Row n of cluster c's tile is atom c + n * (number of clusters): a tile of CONSECUTIVE atoms lies inside one or two
+  // reactions, whose in-degree (n_g - 1 when every pair is inside the cutoff) varies 9 .. 24 at batch 100, so the CTAs'
+  // gather volumes differed by a factor of two and every block waited for the slowest one (8 of 24 us in the in-kernel
+  // timeline profiles/r3_node_chain_timeline.txt); strided rows sample ~14 reactions per CTA.
   const int npc = p.nodes_per_cluster > 0 ? min(p.nodes_per_cluster, NT) : NT;
-  const int node0 = (blockIdx.x / 2) * npc;       // first atom of the cluster's tile
-  const int N = min(p.num_nodes, node0 + npc);    // atoms past the tile belong to the next cluster
+  const int cluster = blockIdx.x / 2, T = gridDim.x / 2;
+  const int N = p.num_nodes;
+  auto atom_of = [&](int n) { return cluster + n * T; };  // valid while n < npc and the result is < N
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
   // layout: B operand 0 | staged in-CSR ids | ring slot 0 | ring slot 1 | B operand 1
@@ -568,23 +574,40 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       const int my0 = rank == 0 ? 0 : na0, my_n = rank == 0 ? na0 : npc - na0;
       // the in-CSR ids: written by the edge build at the start of the step (complete before the first node kernel
       // started), not by the preceding node kernel -- no need to wait for it
-      for (int i = tid; i <= my_n; i += NW) s_ptr[i] = p.in_ptr[min(node0 + my0 + i, N)];
+      // one warp per atom: its in-edge range, then (first warp) the prefix of the counts = the staged positions
+      if (warp == 0) {
+        int cnt = 0;
+        if (lane < my_n) {
+          const int a = atom_of(my0 + lane);
+          const int beg = a < N ? p.in_ptr[a] : 0;
+          cnt = a < N ? p.in_ptr[a + 1] - beg : 0;
+          s_gbeg[lane] = beg;
+        }
+        int inc = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(TSD_FULL_MASK, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (lane < my_n) s_ptr[lane + 1] = inc;
+        if (lane == 0) s_ptr[0] = 0;
+      }
       asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
-      const int seg0 = s_ptr[0], seg_n = s_ptr[my_n] - seg0;
+      const int seg_n = s_ptr[my_n];
       const bool staged = seg_n <= CAP;
       if (staged) {
-        for (int i = tid; i < seg_n; i += NW) {
-          const int e = p.in_eid[seg0 + i];
-          s_eid[i] = e;
-          s_src[i] = p.in_src[seg0 + i];
-          // the filter rows were written by the filter stack tens of microseconds (and ~90 MB) ago: pull them back
-          // into L2 while the preceding node kernel is still running (profiles/r3_pair_gather_cost.txt)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.filt + (size_t)e * H), "r"(H * 4) : "memory");
+        for (int n = warp; n < my_n; n += NU_WORKERS) {
+          const int gb = s_gbeg[n], lb = s_ptr[n], cnt = s_ptr[n + 1] - lb;
+          for (int i = lane; i < cnt; i += 32) {
+            const int e = p.in_eid[gb + i];
+            s_eid[lb + i] = e;
+            s_src[lb + i] = p.in_src[gb + i];
+            // the filter rows were written by the filter stack tens of microseconds (and ~90 MB) ago: pull them back
+            // into L2 while the preceding node kernel is still running (profiles/r3_pair_gather_cost.txt)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.filt + (size_t)e * H), "r"(H * 4) : "memory");
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"r"(NW) : "memory");
       }
-      const int* eids = staged ? s_eid - seg0 : p.in_eid;
-      const int* srcs = staged ? s_src - seg0 : p.in_src;
       const uint32_t x_own = smem_base, x_peer = nu_mapa(smem_base, peer);  // own copy: plain shared-memory stores
       pdl_wait();  // see k_node_update
       pdl_trigger();
@@ -594,8 +617,11 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       for (int item = warp; item < my_n * 2; item += NU_WORKERS) {
         const int n = item >> 1, slab = item & 1;
         const int off = slab * 128 + lane * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the tile: zeros (their output columns are never stored)
-        if (node0 + my0 + n < N) acc = nu_aggregate_item(p, eids, srcs, s_ptr[n], s_ptr[n + 1], off, lane);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past the last atom: zeros (their output columns are never stored)
+        if (atom_of(my0 + n) < N) {
+          if (staged) acc = nu_aggregate_item(p, s_eid, s_src, s_ptr[n], s_ptr[n + 1], off, lane);
+          else acc = nu_aggregate_item(p, p.in_eid, p.in_src, s_gbeg[n], s_gbeg[n] + s_ptr[n + 1] - s_ptr[n], off, lane);
+        }
         const float4 r = tf32_rn4(acc);
         const uint32_t o = (uint32_t)((off >> 5) * X_PANEL) + sw128_off(my0 + n, (off & 31) >> 2);
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(x_own + o), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
@@ -626,7 +652,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       float res[CW];
       if (st_res) {  // independent of the accumulator: in flight behind the MMA
 #pragma unroll
-        for (int j = 0; j < CW; ++j) res[j] = st_res[(size_t)min(node0 + n0 + j, N - 1) * H + f];
+        for (int j = 0; j < CW; ++j) res[j] = st_res[(size_t)min(atom_of(n0 + j), N - 1) * H + f];
       }
       mbar_wait(&bar_acc[b], (uint32_t)((s >> 1) & 1));
       tc_fence_after();
@@ -668,7 +694,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) k_node_pair(const NodeArgs p, c
       if (st_store) {
 #pragma unroll
         for (int j = 0; j < CW; ++j)
-          if (node0 + n0 + j < N) st_store[(size_t)(node0 + n0 + j) * H + f] = r[j];
+          if (n0 + j < npc && atom_of(n0 + j) < N) st_store[(size_t)atom_of(n0 + j) * H + f] = r[j];
       }
       if (tid == 0) NU_STAMP(3 + s);
     }
