@@ -28,8 +28,8 @@ for it in range(2):
     t = phase("warm-up step + graph capture", t)
     runner.run()
     t = phase("5000 replays", t)
-    traj = runner.traj.cpu()
-    t = phase("trajectory D2H (110 MB)", t)
+    traj = runner.traj_cpu()
+    t = phase("trajectory D2H tail (110 MB streamed during the run)", t)
     lst = list(traj.unbind(0))
     t = phase("unbind", t)
     print("%-34s %8.2f ms" % ("total", (t - t_all) * 1e3))

@@ -705,6 +705,39 @@ class LangevinRunner:
             C.pointer(exchange.c) if exchange is not None else None)
         self.use_graph = use_graph
         self.graph = None
+        # the trajectory goes to the host while the loop runs (the reference appends pos.cpu() every step,
+        # sampler.py:246-247): chunks of finished slots, pinned memory, a copy stream beside the replays
+        self._traj_host = None
+        self._copy_stream = None
+        self._done = 0    # steps issued since the last reset
+        self._copied = 0  # trajectory slots handed to the copy stream
+
+    TRAJ_CHUNK = 256
+
+    def _flush_traj(self):
+        a, b = self._copied, min(self._done, self.n_steps)
+        if self.traj is None or b <= a:
+            return
+        if self._traj_host is None:
+            self._traj_host = torch.empty(self.traj.shape, dtype=self.traj.dtype, pin_memory=True)
+            self._copy_stream = torch.cuda.Stream(device=self.plan.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._copy_stream.wait_event(ev)
+        with torch.cuda.stream(self._copy_stream):
+            self._traj_host[a:b].copy_(self.traj[a:b], non_blocking=True)
+        self._copied = b
+
+    @_on_plan_device
+    def traj_cpu(self):
+        """The trajectory (n_steps, N, 3) on the host: the slots of the steps run so far are valid."""
+        if self.traj is None:
+            return None
+        self._flush_traj()
+        if self._traj_host is None:
+            return self.traj.cpu()
+        self._copy_stream.synchronize()
+        return self._traj_host
 
     def _one_step(self):
         lib = L.load()
@@ -722,6 +755,7 @@ class LangevinRunner:
         if self.exchange is not None:
             self.exchange.new_trajectory(self.n_steps)
         self.pos.copy_(self.pos0)
+        self._done = self._copied = 0
         self.step_counter.zero_()
         self.ticket.zero_()
         self.nan_flag.zero_()
@@ -754,6 +788,9 @@ class LangevinRunner:
                 self.graph.replay()
             else:
                 self._one_step()
+            self._done += 1
+            if self.traj is not None and self._done - self._copied >= self.TRAJ_CHUNK:
+                self._flush_traj()
             if check_every and (k + 1) % check_every == 0 and int(self.nan_flag.item()):
                 self._raise_flag()
         if int(self.nan_flag.item()):

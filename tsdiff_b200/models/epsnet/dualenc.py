@@ -230,7 +230,7 @@ class DualEncoderEpsNetwork(nn.Module):
                                       clip_pos=clip_pos, keep_traj=kwargs.get("keep_traj", True),
                                       use_graph=kwargs.get("use_graph", True), rule=L.RULE_DSM)
             pos = runner.run()
-            return pos, (list(runner.traj.cpu().unbind(0)) if runner.traj is not None else [])
+            return pos, (list(runner.traj_cpu().unbind(0)) if runner.traj is not None else [])
         sampling_type = kwargs.get("sampling_type", "ddpm_noisy")
         if sampling_type not in ("ld", "ddpm_noisy", "ddpm_det", "generalized"):
             raise NotImplementedError("sampling_type %r (dualenc.py:861-952 has ld, ddpm_noisy, ddpm_det, generalized)"
@@ -249,5 +249,5 @@ class DualEncoderEpsNetwork(nn.Module):
                                   keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True),
                                   rule=rule)
         pos = runner.run()
-        traj = list(runner.traj.cpu().unbind(0)) if runner.traj is not None else []
+        traj = list(runner.traj_cpu().unbind(0)) if runner.traj is not None else []
         return pos, traj

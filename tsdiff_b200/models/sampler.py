@@ -96,7 +96,7 @@ class EnsembleSampler(nn.Module):
                                   keep_traj=kwargs.get("keep_traj", True), use_graph=kwargs.get("use_graph", True),
                                   rule=rule)
         pos = runner.run()
-        traj = list(runner.traj.cpu().unbind(0)) if runner.traj is not None else []
+        traj = list(runner.traj_cpu().unbind(0)) if runner.traj is not None else []
         if exchange is not None:
             del runner
             exchange.close()
