@@ -705,8 +705,11 @@ class LangevinRunner:
             C.pointer(exchange.c) if exchange is not None else None)
         self.use_graph = use_graph
         self.graph = None
-        # the trajectory goes to the host while the loop runs (the reference appends pos.cpu() every step,
-        # sampler.py:246-247): chunks of finished slots, pinned memory, a copy stream beside the replays
+        # The trajectory goes to the host while the loop runs (the reference appends pos.cpu() every step,
+        # sampler.py:246-247): finished slots in chunks, on a copy stream beside the replays, into a pinned host tensor
+        # (torch's caching host allocator recycles it between calls).  Nothing of the 110 MB is left to copy when the
+        # loop ends.  (Staging through two small pinned buffers into a pageable tensor measured unstable end to end:
+        # profiles/r3_e2e_phases.txt.)
         self._traj_host = None
         self._copy_stream = None
         self._done = 0    # steps issued since the last reset
@@ -784,6 +787,8 @@ class LangevinRunner:
         n = self.n_steps if n_steps is None else n_steps
         self.prepare()
         for k in range(n):
+            # (a graph of 8 consecutive steps saved 2 us per step of launch gap, but its capture / destruction cost more
+            # per dynamic_sampling call than 5000 steps gain: profiles/r3_e2e_phases.txt)
             if self.graph is not None:
                 self.graph.replay()
             else:
