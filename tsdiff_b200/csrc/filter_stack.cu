@@ -18,15 +18,15 @@
 //                acc1 (tcgen05.st): X never leaves tensor memory, the second GEMM takes its A operand from
 //                TMEM.  Handed to the MMA issuer K panel by K panel (32 columns), so the second GEMM trails the
 //                activation by a panel instead of waiting for all of it.
-//   warps 18..25 epi2 (two warps per TMEM lane quarter = 32 rows, even / odd output panels): acc2 -> + b2 -> * C(len)
-//                -> 32 x 32 block in the warp's own 4 KiB staging -> TMA store (1.2 us per block: the stores queue
+//   warps 18..29 epi2 (three warps per TMEM lane quarter = 32 rows, 16-column units u % 3): acc2 -> + b2 -> * C(len)
+//                -> 32 x 16 block in the warp's own 2 KiB staging -> TMA store (1.2 us per 32 x 32 block: the stores queue
 //                behind the weight loads of the same SM; reading the block back and storing whole 128-byte lines
 //                with st.global measured slower still, 1.75 us per block:
 //                profiles/r3_filter_stack_timeline_{tma_store,st_global}.txt).  No CTA-level barrier anywhere; it
 //                overlaps the NEXT layer's first GEMM and activation (the MMA issuer waits on `acc2_free`
 //                before it overwrites acc2).
 //
-// Shared memory (H = 256): 4 ring slots x 48 KiB + 8 x 4 KiB staging (the ring depth is what the weight
+// Shared memory (H = 256): 4 ring slots x 48 KiB + 12 x 2 KiB staging (the ring depth is what the weight
 // stream's throughput hangs on: with X in shared memory there was room for 2 slots = 96 KiB in flight and the
 // stream reached 61 of the 127 GB/s one SM can ingest; profiles/r3_filter_stack_timeline_smemX.txt).
 // TMEM: all 512 columns.
@@ -50,9 +50,9 @@ __device__ unsigned long long g_fs_dbg[256];
 
 constexpr int FS_EPI_WARPS = 16;
 constexpr int FS_EPI_THREADS = FS_EPI_WARPS * 32;
-constexpr int FS_STORE_WARPS = 8;
+constexpr int FS_STORE_WARPS = 12;
 constexpr int FS_THREADS = (FS_EPI_WARPS + 2 + FS_STORE_WARPS) * 32;
-constexpr int FS_STAGE_BYTES = FS_STORE_WARPS * 32 * TC_BK * 4;  // per store warp 32 rows x 128 B
+constexpr int FS_STAGE_BYTES = FS_STORE_WARPS * 32 * 16 * 4;  // per store warp 32 rows x 64 B (half an output panel)
 constexpr int FS_MAX_SLOTS = 6;
 int g_fs_grid = 0;  // tuning hook of profiles/scripts: CTA count (0 = one per SM)
 
@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
     const bool stamp = warp == FS_EPI_WARPS + 2 && lane == 0;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint8_t* const buf = stage + (size_t)(warp - (FS_EPI_WARPS + 2)) * (32 * TC_BK * 4);
-    const int kb0 = (warp - (FS_EPI_WARPS + 2)) >> 2;  // this warp's panels: kb0, kb0 + 2, ...
+    uint8_t* const buf = stage + (size_t)(warp - (FS_EPI_WARPS + 2)) * (32 * 16 * 4);
+    const int u0 = (warp - (FS_EPI_WARPS + 2)) >> 2;  // this warp's 16-column units of the output: u0, u0 + 3, ...
     int it = 0;
     for (int item = blockIdx.x; item < items; item += stride, ++it) {
       const int l = item / tiles, m0 = (item - l * tiles) * TC_BM;
@@ -275,23 +275,23 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_filter_stack(const FsArgsDev 
       tc_fence_after();
       if (stamp) FS_STAMP(16 * l + 5);
 #pragma unroll 1
-      for (int kb = kb0; kb < NKB; kb += FS_STORE_WARPS / 4) {
-        uint32_t v[32];
-        tmem_ld32(acc2 + lane_addr + (uint32_t)(kb * TC_BK), v);
+      for (int u = u0; u < H / 16; u += FS_STORE_WARPS / 4) {
+        uint32_t v[16];
+        tmem_ld_cols<16>(acc2 + lane_addr + (uint32_t)(u * 16), v);
         if (lane == 0) tma_store_wait_read();  // this warp's previous store has read the staging block
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < TC_BK / 4; ++c) {
-          const float4 b = b2 ? __ldg(reinterpret_cast<const float4*>(b2 + kb * TC_BK + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 4; ++c) {
+          const float4 b = b2 ? __ldg(reinterpret_cast<const float4*>(b2 + u * 16 + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 o = make_float4((__uint_as_float(v[4 * c + 0]) + b.x) * cscale, (__uint_as_float(v[4 * c + 1]) + b.y) * cscale,
                                  (__uint_as_float(v[4 * c + 2]) + b.z) * cscale, (__uint_as_float(v[4 * c + 3]) + b.w) * cscale);
           if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(buf + sw128_off(lane, c)) = o;
+          *reinterpret_cast<float4*>(buf + sw64_off(lane, c)) = o;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA store reads
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&maps.out[l], buf, kb * TC_BK, m0 + q * 32);
+          tma_store_2d(&maps.out[l], buf, u * 16, m0 + q * 32);
           tma_store_commit();
         }
       }
@@ -369,7 +369,7 @@ int tsd_filter_stack_tf32(const FilterStackArgs& a, cudaStream_t stream) {
       return TSD_ERR_UNSUPPORTED;
     if (!make_tensor_map(&maps.w[2 * l], y.W0, (uint64_t)a.H, (uint64_t)a.H, (uint32_t)a.H) ||
         !make_tensor_map(&maps.w[2 * l + 1], y.W2, (uint64_t)a.H, (uint64_t)a.H, (uint32_t)a.H) ||
-        !make_tensor_map(&maps.out[l], y.out, (uint64_t)a.M_cap, (uint64_t)a.H, 32))  // one store warp's block
+        !make_tensor_map(&maps.out[l], y.out, (uint64_t)a.M_cap, (uint64_t)a.H, 32, 16))  // one store warp's block
       return TSD_ERR_UNSUPPORTED;
     d.layer[l].b0 = y.b0;
     d.layer[l].b2 = y.b2;

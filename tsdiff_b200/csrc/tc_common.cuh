@@ -279,17 +279,20 @@ static inline EncodeTiledFn encode_tiled_fn() {
 }
 
 // row-major fp32 matrix (rows x cols), box = box_rows x 32 floats, SWIZZLE_128B
-static inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// (box_cols = 16: 64-byte rows, SWIZZLE_64B -- 16-byte chunk c of row r sits at r * 64 + ((c ^ ((r >> 1) & 3)) << 4))
+static inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                   uint32_t box_cols = TC_BK) {
   EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) return false;
+  if (!enc || !(box_cols == TC_BK || box_cols == 16)) return false;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * sizeof(float)};
-  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estride[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+__device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 
 
