@@ -654,6 +654,9 @@ class PeerExchange:
             lib.tsd_peer_free(C.c_void_p(self._owned))
             self._owned = None
 
+_TRAJ_STAGING = {}  # device index -> ([two flat pinned float32 buffers], copy stream): LangevinRunner._staging
+
+
 class LangevinRunner:
     """Runs the Langevin loop for either engine: per step [K2, eps-net kernels, K7], captured
     once in a CUDA graph and replayed; per-step scalars come from a device table indexed by
@@ -706,30 +709,60 @@ class LangevinRunner:
         self.use_graph = use_graph
         self.graph = None
         # The trajectory goes to the host while the loop runs (the reference appends pos.cpu() every step,
-        # sampler.py:246-247): finished slots in chunks, on a copy stream beside the replays, into a pinned host tensor
-        # (torch's caching host allocator recycles it between calls).  Nothing of the 110 MB is left to copy when the
-        # loop ends.  (Staging through two small pinned buffers into a pageable tensor measured unstable end to end:
-        # profiles/r3_e2e_phases.txt.)
+        # sampler.py:246-247): finished slots in chunks, device -> one of two pinned staging buffers on a copy stream
+        # beside the replays, then staging -> the caller's tensor on the host thread, which runs ahead of the GPU anyway.
+        # Nothing of the 110 MB is left to copy when the loop ends.  The staging buffers and the stream are allocated once
+        # per process and device (_TRAJ_STAGING): allocating / freeing pinned memory per call cost 20 - 600 ms depending
+        # on the box (profiles/r3_e2e_phases.txt).  One trajectory at a time per device uses them.
         self._traj_host = None
-        self._copy_stream = None
-        self._done = 0    # steps issued since the last reset
-        self._copied = 0  # trajectory slots handed to the copy stream
+        self._pending = []  # (first slot, last slot, staging index, copy-done event), oldest first
+        self._done = 0      # steps issued since the last reset
+        self._copied = 0    # trajectory slots handed to the copy stream
 
     TRAJ_CHUNK = 256
 
+    def _staging(self):
+        dev = torch.device(self.plan.device)
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        rows = 2 * self.TRAJ_CHUNK
+        need = rows * max(self.plan.num_nodes, 1) * 3
+        st = _TRAJ_STAGING.get(key)
+        if st is None or st[0][0].numel() < need:
+            cap = max(need, 1 << 22)  # >= 16 MB each: batches of up to ~2700 atoms share one allocation
+            flat = [torch.empty(cap, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            st = (flat, st[1] if st is not None else torch.cuda.Stream(device=dev))
+            _TRAJ_STAGING[key] = st
+        bufs = [f[:need].view(rows, max(self.plan.num_nodes, 1), 3) for f in st[0]]
+        return bufs, st[1]
+
+    def _drain(self, keep):
+        """staging -> host tensor for all but the newest `keep` chunks in flight"""
+        while len(self._pending) > keep:
+            a, b, i, done = self._pending.pop(0)
+            done.synchronize()
+            self._traj_host[a:b].copy_(self._staging()[0][i][: b - a])
+
     def _flush_traj(self):
-        a, b = self._copied, min(self._done, self.n_steps)
-        if self.traj is None or b <= a:
+        if self.traj is None:
             return
+        bufs, copy_stream = self._staging()
         if self._traj_host is None:
-            self._traj_host = torch.empty(self.traj.shape, dtype=self.traj.dtype, pin_memory=True)
-            self._copy_stream = torch.cuda.Stream(device=self.plan.device)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self._copy_stream.wait_event(ev)
-        with torch.cuda.stream(self._copy_stream):
-            self._traj_host[a:b].copy_(self.traj[a:b], non_blocking=True)
-        self._copied = b
+            self._traj_host = torch.empty(self.traj.shape, dtype=self.traj.dtype)
+        end = min(self._done, self.n_steps)
+        while self._copied < end:
+            a = self._copied
+            b = min(end, a + bufs[0].size(0))
+            self._drain(1)  # the staging buffer used two chunks ago is free again
+            i = 0 if not self._pending else 1 - self._pending[-1][2]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            copy_stream.wait_event(ev)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(copy_stream):
+                bufs[i][: b - a].copy_(self.traj[a:b], non_blocking=True)
+                done.record(copy_stream)
+            self._pending.append((a, b, i, done))
+            self._copied = b
 
     @_on_plan_device
     def traj_cpu(self):
@@ -737,9 +770,7 @@ class LangevinRunner:
         if self.traj is None:
             return None
         self._flush_traj()
-        if self._traj_host is None:
-            return self.traj.cpu()
-        self._copy_stream.synchronize()
+        self._drain(0)
         return self._traj_host
 
     def _one_step(self):
@@ -758,6 +789,7 @@ class LangevinRunner:
         if self.exchange is not None:
             self.exchange.new_trajectory(self.n_steps)
         self.pos.copy_(self.pos0)
+        self._drain(0)
         self._done = self._copied = 0
         self.step_counter.zero_()
         self.ticket.zero_()
