@@ -654,7 +654,7 @@ class PeerExchange:
             lib.tsd_peer_free(C.c_void_p(self._owned))
             self._owned = None
 
-_TRAJ_STAGING = {}  # device index -> ([two flat pinned float32 buffers], copy stream): LangevinRunner._staging
+_TRAJ_STAGING = {}  # device index -> ([two flat pinned float32 buffers], copy stream, weakref of the last user)
 
 
 class LangevinRunner:
@@ -727,11 +727,19 @@ class LangevinRunner:
         rows = 2 * self.TRAJ_CHUNK
         need = rows * max(self.plan.num_nodes, 1) * 3
         st = _TRAJ_STAGING.get(key)
+        # another runner with chunks still in the buffers (two trajectories advanced alternately): finish its copies first
+        other = st[2]() if st is not None and st[2] is not None else None
+        if other is not None and other is not self and other._pending:
+            other._drain(0)
+            st = _TRAJ_STAGING.get(key)
         if st is None or st[0][0].numel() < need:
             cap = max(need, 1 << 22)  # >= 16 MB each: batches of up to ~2700 atoms share one allocation
             flat = [torch.empty(cap, dtype=torch.float32, pin_memory=True) for _ in range(2)]
-            st = (flat, st[1] if st is not None else torch.cuda.Stream(device=dev))
-            _TRAJ_STAGING[key] = st
+            st = (flat, st[1] if st is not None else torch.cuda.Stream(device=dev), None)
+        if st[2] is None or st[2]() is not self:
+            import weakref
+            st = (st[0], st[1], weakref.ref(self))
+        _TRAJ_STAGING[key] = st
         bufs = [f[:need].view(rows, max(self.plan.num_nodes, 1), 3) for f in st[0]]
         return bufs, st[1]
 
