@@ -2,18 +2,18 @@
 //
 //   filt_l = nn2_l(ssp(nn0_l(edge_attr))) * C(len)        l = 0 .. L-1        (schnet.py:91-98)
 //
-// Every block's filter network reads the same edge_attr and nothing else, so one CTA keeps a 128-row
-// tile and runs the 2 L chained GEMMs back to back.  Round 1/2 launched one two-GEMM kernel per block
-// (gemm_chain.cu, k_chain_tf32<0>): main loop -> epilogue -> main loop -> epilogue in strict sequence,
-// 7 launches of 22-30 us each on the step's critical path (profiles/r2_kineto_step_tf32.txt).  Here the
-// roles run concurrently and only meet at mbarriers:
+// Every block's filter network reads the same edge_attr and nothing else, so the work items (block, 128-row tile)
+// are independent: the kernel is persistent, one CTA per SM, CTA b takes items b, b + gridDim.x, ... (block-major;
+// 658 items on 148 SMs at batch 100).  Round 1/2 launched one two-GEMM kernel per block (gemm_chain.cu,
+// k_chain_tf32<0>): 94 CTAs, main loop -> epilogue -> main loop -> epilogue in strict sequence, 7 launches of 22-30 us
+// each (profiles/r2_kineto_step_tf32.txt).  Here, per item, the roles run concurrently and only meet at mbarriers:
 //
-//   warp 16      TMA producer: per layer the tile's 8 edge_attr panels + the 8 panels of W0, then the
+//   warp 16      TMA producer: per item the tile's 8 edge_attr panels + the 8 panels of W0, then the
 //                8 panels of W2, through a ring of {W panel, A panel} slots.  One SM ingests 64 B/clk
 //                from L2 (profiles/r2_tma_stream.txt), exactly what the tensor pipe consumes per
 //                M128 x N256 x K8 tf32 MMA of streamed W -- the ring must never drain.
 //   warp 17      MMA issuer: acc1 = A . W0^T (TMEM columns [0,H)), then acc2 = X . W2^T (columns [H,2H))
-//                panel by panel as soon as the epilogue warps have produced the matching QUARTER of X.
+//                panel by panel as soon as the activation warps have produced the matching K panel of X.
 //   warps 0..15  epilogues.  epi1: acc1 -> + b0 -> shifted softplus -> TF32 (RNE) -> written back IN PLACE over
 //                acc1 (tcgen05.st): X never leaves tensor memory, the second GEMM takes its A operand from
 //                TMEM.  Handed to the MMA issuer K panel by K panel (32 columns), so the second GEMM trails the
@@ -23,7 +23,7 @@
 //                behind the weight loads of the same SM; reading the block back and storing whole 128-byte lines
 //                with st.global measured slower still, 1.75 us per block:
 //                profiles/r3_filter_stack_timeline_{tma_store,st_global}.txt).  No CTA-level barrier anywhere; it
-//                overlaps the NEXT layer's first GEMM and activation (the MMA issuer waits on `acc2_free`
+//                overlaps the NEXT item's first GEMM and activation (the MMA issuer waits on `acc2_free`
 //                before it overwrites acc2).
 //
 // Shared memory (H = 256): 4 ring slots x 48 KiB + 12 x 2 KiB staging (the ring depth is what the weight

@@ -26,6 +26,10 @@
 //   warp 16      TMA producer: W panels (H rows x 32 floats) of ALL stages through the ring; it does
 //                not depend on the atoms, so it starts streaming at kernel start, behind the aggregation
 //   warp 17      MMA issuer (one lane): per K panel 4 x (H/128) tcgen05.mma M128 x NT x K8 kind::tf32
+//
+// Two kernels: k_node_update<H, NT, C> (one GEMM CTA per tile, optionally C - 1 helper CTAs that only aggregate) and,
+// further down, k_node_pair<NT> (H = 256: both CTAs of a 2-CTA cluster run the GEMMs, each on half of the output
+// features -- what the Langevin step uses).  node_chain.cu holds the persistent variant over all blocks (off by default).
 #include <string.h>
 
 #include "tc_common.cuh"
