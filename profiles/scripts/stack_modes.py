@@ -29,7 +29,7 @@ for spec in specs:
     lib.tsd_tune_gemm_chain2(chain2)
     ctas2 = f[7] if len(f) > 7 else 0
     lib.tsd_tune_filter_stack_ctas2(ctas2)
-    nchain = f[8] if len(f) > 8 else 1
+    nchain = f[8] if len(f) > 8 else 0
     lib.tsd_tune_node_chain(nchain)
     lib.tsd_tune_filter_stack(mode)
     lib.tsd_tune_node_tile(tile)
