@@ -453,11 +453,7 @@ struct EncoderFork {
   int init(int num_blocks) {
     if (num_blocks > MAX_BLOCKS) return TSD_ERR_UNSUPPORTED;
     if (ready) return TSD_OK;
-    // (a first call under stream capture cannot allocate: the node chain then stays one kernel per block)
-    if (cudaMalloc(&nc_words, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(nc_words, 0, 8) != cudaSuccess) {
-      (void)cudaGetLastError();
-      nc_words = nullptr;
-    }
+
     // the node-side chain is serial and short (15-CTA kernels): give it the highest priority so its
     // CTAs are scheduled as soon as an SM frees up instead of queueing behind the edge tiles
     int prio_lo = 0, prio_hi = 0;
@@ -687,6 +683,18 @@ extern "C" int tsd_schnet_encoder(const tsd_batch_t* batch, const tsd_edges_t* e
     const int tile = tsd_node_tile(stacked && stack_cut == num_blocks, batch->num_nodes, &npc);
     // Behind the complete filter stack the node side of ALL blocks is one persistent kernel (node_chain.cu) when every
     // cluster can be resident at once; otherwise one node kernel per block below.
+    if (stacked && stack_cut == num_blocks && tile == 323 && H == 256 && g_node_chain && !fk.nc_words) {
+      // the chain's two device words, allocated on first use -- never under stream capture (an allocation would
+      // invalidate the capture): a first call inside a capture keeps one kernel per block
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+        if (cudaMalloc(&fk.nc_words, 2 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(fk.nc_words, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
+          (void)cudaGetLastError();
+          fk.nc_words = nullptr;
+        }
+      }
+    }
     if (stacked && stack_cut == num_blocks && tile == 323 && H == 256 && g_node_chain && fk.nc_words &&
         num_blocks <= TSD_NC_MAX_BLOCKS) {
       NodeChainArgs ca;
